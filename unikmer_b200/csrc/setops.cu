@@ -1,0 +1,611 @@
+// setops.cu -- union / inter / diff / common / merge on sorted k-mer streams.
+//
+// Replaces the inner loops of union.go:186-208,260-305; inter.go:188-286;
+// diff.go:136-146,341-515,566-594; common.go:220-283,329-354 and the heap merge
+// mergeChunksFile (util-sort.go:227-606).  The reference's hash maps / two-pointer
+// walks / binary heap become one kernel family: a merge-path partitioned, shared-memory
+// tiled two-way set operation with single-pass output (decoupled look-back), applied in
+// file order (inter, diff: exactly the reference's iteration) or as a balanced tree
+// (union, common, merge).
+//
+// Data layout: SoA -- keys uint64[n], taxids uint32[n] (optional), counts uint32[n]
+// (common only).  One CTA per tile of ~THREADS*VT merged elements: the two input slices
+// are brought into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier),
+// every thread walks VT merged elements with the reference's three-way compare, outputs
+// are compacted through shared memory and written as contiguous runs.
+#include "common.cuh"
+#include "lca.cuh"
+
+namespace {
+
+enum SetOp { OP_INTER = 0, OP_DIFF = 1, OP_UNION = 2, OP_MERGE = 3 };
+
+constexpr int SO_THREADS = 256;
+constexpr int SO_VT = 15;                    // merged elements per thread (loop runs VT+1 steps)
+constexpr int SO_TILE = SO_THREADS * SO_VT;  // merged elements per tile (+-1 after pairing)
+
+// number of A elements among the first `diag` merged elements; ties: A first
+template <typename KA, typename KB>
+__device__ __forceinline__ int merge_path(KA a, int na, KB b, int nb, int diag) {
+    int lo = diag > nb ? diag - nb : 0;
+    int hi = diag < na ? diag : na;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] <= b[diag - 1 - mid]) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ long long merge_path_global(const uint64_t* __restrict__ a, long long na, const uint64_t* __restrict__ b,
+                                                       long long nb, long long diag) {
+    long long lo = diag > nb ? diag - nb : 0;
+    long long hi = diag < na ? diag : na;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (a[mid] <= b[diag - 1 - mid]) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// tile boundaries: part[2t] = A index, part[2t+1] = B index of the first element of tile t.
+// For the pairing ops an equal (A,B) pair is never split: the B twin joins the A side's tile.
+__global__ void setop_partition_kernel(const uint64_t* __restrict__ A, long long nA, const uint64_t* __restrict__ B, long long nB,
+                                       int num_tiles, int pairing, long long* __restrict__ part, int* __restrict__ err) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > num_tiles) return;
+    long long total = nA + nB;
+    long long diag = (long long)t * SO_TILE;
+    if (diag > total) diag = total;
+    long long a = merge_path_global(A, nA, B, nB, diag);
+    long long b = diag - a;
+    if (pairing) {
+        if (a > 0 && b < nB && A[a - 1] == B[b]) ++b;
+        // contract check at the tile seams (inside tiles the walk checks it)
+        if (a > 0 && a < nA && A[a - 1] >= A[a]) atomicExch(err, (int)UKM_E_NOT_SORTED_UNIQUE);
+        if (b > 0 && b < nB && B[b - 1] >= B[b]) atomicExch(err, (int)UKM_E_NOT_SORTED_UNIQUE);
+    }
+    part[2 * t] = a;
+    part[2 * t + 1] = b;
+}
+
+// One thread issues the loads of elements [start, start+count) of g into shared memory so that
+// element start+i lands in s[h + i], h = misalignment of the first element in elements.  The
+// 16-byte aligned body goes through one TMA bulk copy; the (< 16 B) head and tail through plain
+// loads.  Returns the bytes the mbarrier has to expect.
+template <typename T>
+__device__ __forceinline__ int slice_offset(const T* g, long long start) {
+    return (int)((reinterpret_cast<uintptr_t>(g + start) & 15u) / sizeof(T));
+}
+template <typename T>
+__device__ __forceinline__ unsigned slice_body_bytes(const T* g, long long start, int count) {
+    constexpr int PER16 = 16 / sizeof(T);
+    int h = slice_offset(g, start);
+    int head = h ? (PER16 - h) : 0;
+    if (head > count) head = count;
+    int body = ((count - head) / PER16) * PER16;
+    return (unsigned)(body * sizeof(T));
+}
+template <typename T>
+__device__ __forceinline__ void slice_issue(T* s, const T* g, long long start, int count, uint64_t* bar) {
+    constexpr int PER16 = 16 / sizeof(T);
+    int h = slice_offset(g, start);
+    int head = h ? (PER16 - h) : 0;
+    if (head > count) head = count;
+    int body = ((count - head) / PER16) * PER16;
+    for (int i = 0; i < head; ++i) s[h + i] = g[start + i];
+    if (body) tma_load_1d(s + h + head, g + start + head, (unsigned)(body * sizeof(T)), bar);
+    for (int i = head + body; i < count; ++i) s[h + i] = g[start + i];
+}
+
+struct SetopArgs {
+    const uint64_t* A;
+    const uint32_t* tA;
+    const uint32_t* cA;
+    long long nA;
+    const uint64_t* B;
+    const uint32_t* tB;
+    const uint32_t* cB;
+    long long nB;
+    const long long* part;
+    uint64_t* outK;
+    uint32_t* outT;
+    uint32_t* outC;
+    uint64_t* status;        // look-back words, one per tile
+    uint32_t* tile_counter;  // dynamic tile ids
+    unsigned long long* total_out;
+    int num_tiles;
+    unsigned flags;      // UKM_F_MIX_TAXID | UKM_F_COMPARE_TAXID
+    uint32_t threshold;  // OP_UNION with counts: emit only (count & 0xffff) >= threshold (0 = all)
+    TaxDev tax;
+    int* err;
+};
+
+template <int OP, bool TAX, bool CNT>
+__global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
+    constexpr int T = SO_TILE;
+    constexpr int NW = SO_THREADS / 32;
+    // dynamic shared memory: keys of both slices (each with up to 1 slot of alignment slack, B on
+    // an even slot), then taxids, then counts (4-element alignment slack each)
+    extern __shared__ __align__(16) unsigned char so_smem[];
+    uint64_t* s_k = reinterpret_cast<uint64_t*>(so_smem);                          // T + 8
+    uint32_t* s_t = reinterpret_cast<uint32_t*>(s_k + T + 8);                      // T + 20 (TAX)
+    uint32_t* s_c = s_t + (TAX ? T + 20 : 0);                                      // T + 20 (CNT)
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_part[SO_THREADS + 1];  // packed (a << 16 | b) thread starts
+    __shared__ unsigned s_scan[NW + 2];
+    __shared__ int s_tile;
+    __shared__ unsigned long long s_prefix;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_tile = (int)atomicAdd(p.tile_counter, 1u);
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int tile = s_tile;
+    const long long a_lo = p.part[2 * tile], b_lo = p.part[2 * tile + 1];
+    const int na = (int)(p.part[2 * tile + 2] - a_lo), nb = (int)(p.part[2 * tile + 3] - b_lo);
+
+    // shared-memory placement of the two slices
+    const int hA = slice_offset(p.A, a_lo);
+    const int offB = ((hA + na + 1) & ~1) + slice_offset(p.B, b_lo);
+    int hAt = 0, offBt = 0, hAc = 0, offBc = 0;
+    if (TAX) {
+        hAt = slice_offset(p.tA, a_lo);
+        offBt = ((hAt + na + 3) & ~3) + slice_offset(p.tB, b_lo);
+    }
+    if (CNT) {
+        hAc = p.cA ? slice_offset(p.cA, a_lo) : 0;
+        offBc = ((hAc + na + 3) & ~3) + (p.cB ? slice_offset(p.cB, b_lo) : 0);
+    }
+    if (tid == 0) {
+        unsigned bytes = slice_body_bytes(p.A, a_lo, na) + slice_body_bytes(p.B, b_lo, nb);
+        if (TAX) bytes += slice_body_bytes(p.tA, a_lo, na) + slice_body_bytes(p.tB, b_lo, nb);
+        if (CNT) {
+            if (p.cA) bytes += slice_body_bytes(p.cA, a_lo, na);
+            if (p.cB) bytes += slice_body_bytes(p.cB, b_lo, nb);
+        }
+        mbar_expect_tx(&s_bar, bytes);
+        slice_issue(s_k, p.A, a_lo, na, &s_bar);
+        slice_issue(s_k + offB - slice_offset(p.B, b_lo), p.B, b_lo, nb, &s_bar);
+        if (TAX) {
+            slice_issue(s_t, p.tA, a_lo, na, &s_bar);
+            slice_issue(s_t + offBt - slice_offset(p.tB, b_lo), p.tB, b_lo, nb, &s_bar);
+        }
+        if (CNT) {
+            if (p.cA) slice_issue(s_c, p.cA, a_lo, na, &s_bar);
+            if (p.cB) slice_issue(s_c + offBc - slice_offset(p.cB, b_lo), p.cB, b_lo, nb, &s_bar);
+        }
+    }
+    if (!mbar_wait(&s_bar, 0)) {
+        if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+    }
+    __syncthreads();  // also publishes thread 0's plain head/tail stores
+
+    const uint64_t* sA = s_k + hA;
+    const uint64_t* sB = s_k + offB;
+    const uint32_t* sTA = s_t + hAt;
+    const uint32_t* sTB = s_t + offBt;
+    const uint32_t* sCA = s_c + hAc;
+    const uint32_t* sCB = s_c + offBc;
+
+    // per-thread start on the merge path of the tile
+    const int total = na + nb;
+    {
+        int diag = tid * SO_VT;
+        if (diag > total) diag = total;
+        int a = merge_path(sA, na, sB, nb, diag);
+        int b = diag - a;
+        if (OP != OP_MERGE) {
+            if (a > 0 && b < nb && sA[a - 1] == sB[b]) ++b;
+        }
+        s_part[tid] = (a << 16) | b;
+        if (tid == 0) s_part[SO_THREADS] = (na << 16) | nb;
+    }
+    __syncthreads();
+    int ai = s_part[tid] >> 16, bi = s_part[tid] & 0xffff;
+    const int a1 = s_part[tid + 1] >> 16, b1 = s_part[tid + 1] & 0xffff;
+
+    // the reference's three-way compare walk (inter.go:228-257, diff.go:395-431), VT+1 steps
+    uint64_t outk[SO_VT + 1];
+    uint32_t outt[TAX ? SO_VT + 1 : 1];
+    uint32_t outc[CNT ? SO_VT + 1 : 1];
+    unsigned emitmask = 0;
+    bool bad = false;
+    if (OP != OP_MERGE) {
+        if (ai > 0 && ai < na && sA[ai - 1] >= sA[ai]) bad = true;
+        if (bi > 0 && bi < nb && sB[bi - 1] >= sB[bi]) bad = true;
+    }
+    uint64_t ka = ai < a1 ? sA[ai] : 0ull, kb = bi < b1 ? sB[bi] : 0ull;
+#pragma unroll
+    for (int it = 0; it <= SO_VT; ++it) {
+        const bool va = ai < a1, vb = bi < b1;
+        const bool eq = va && vb && ka == kb;
+        const bool takeA = va && (!vb || ka <= kb);
+        const bool takeB = vb && !takeA;
+        bool emit;
+        uint64_t k = takeA ? ka : kb;
+        uint32_t tx = 0, cn = 0;
+        if (OP == OP_INTER) {
+            emit = eq;
+            if (TAX && eq) {
+                uint32_t qa = sTA[ai], qb = sTB[bi];
+                if (p.flags & UKM_F_MIX_TAXID) tx = qa == 0 ? qb : (qb == 0 ? qa : lca_dev(p.tax, qa, qb));
+                else tx = lca_dev(p.tax, qa, qb);
+            }
+        } else if (OP == OP_DIFF) {
+            emit = takeA && !eq;
+            if (TAX && takeA) {
+                tx = sTA[ai];
+                if (eq && (p.flags & UKM_F_COMPARE_TAXID)) {
+                    uint32_t qb = sTB[bi];  // keep: same taxid, or subject taxid below the query's
+                    if (tx == qb || lca_dev(p.tax, qb, tx) == tx) emit = true;
+                }
+            }
+        } else if (OP == OP_UNION) {
+            emit = takeA || takeB;
+            if (TAX && emit) {
+                if (eq) tx = lca_dev(p.tax, sTA[ai], sTB[bi]);
+                else tx = takeA ? sTA[ai] : sTB[bi];
+            }
+            if (CNT && emit) {
+                uint32_t ca = takeA ? (p.cA ? sCA[ai] : 1u) : 0u;
+                uint32_t cb = (takeB || eq) ? (p.cB ? sCB[bi] : 1u) : 0u;
+                cn = ca + cb;
+                if (p.threshold && (cn & 0xffffu) < p.threshold) emit = false;
+            }
+        } else {  // OP_MERGE: keep everything, A first on ties
+            emit = takeA || takeB;
+            if (TAX && emit) tx = takeA ? sTA[ai] : sTB[bi];
+        }
+        outk[it] = k;
+        if (TAX) outt[it] = tx;
+        if (CNT) outc[it] = cn;
+        if (emit) emitmask |= 1u << it;
+        // advance
+        const bool advB = takeB || (eq && OP != OP_MERGE);
+        if (takeA) {
+            ++ai;
+            uint64_t nk = ai < a1 ? sA[ai] : 0ull;
+            if (OP != OP_MERGE && ai < a1 && nk <= ka) bad = true;
+            ka = nk;
+        }
+        if (advB) {
+            ++bi;
+            uint64_t nk = bi < b1 ? sB[bi] : 0ull;
+            if (OP != OP_MERGE && bi < b1 && nk <= kb) bad = true;
+            kb = nk;
+        }
+    }
+    if (bad) atomicExch(p.err, (int)UKM_E_NOT_SORTED_UNIQUE);
+
+    // compact through shared memory (the input slices are dead after the barrier inside the scan)
+    const unsigned cnt = (unsigned)__popc(emitmask);
+    unsigned tile_total;
+    const unsigned off = block_excl_scan_u32<SO_THREADS>(cnt, s_scan, &tile_total);
+    if (tid < 32) {
+        unsigned long long prefix;
+        if (OP == OP_MERGE) prefix = (unsigned long long)(a_lo + b_lo);
+        else prefix = lookback_warp(p.status, tile, tile_total, p.err);
+        if (tid == 0) {
+            s_prefix = prefix;
+            if (tile == p.num_tiles - 1) *p.total_out = prefix + tile_total;
+        }
+    }
+    {
+        unsigned o = off;
+#pragma unroll
+        for (int it = 0; it <= SO_VT; ++it) {
+            if (emitmask & (1u << it)) {
+                s_k[o] = outk[it];
+                if (TAX) s_t[o] = outt[it];
+                if (CNT) s_c[o] = outc[it];
+                ++o;
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned long long base = s_prefix;
+    for (unsigned i = tid; i < tile_total; i += SO_THREADS) {
+        p.outK[base + i] = s_k[i];
+        if (TAX) p.outT[base + i] = s_t[i];
+        if (CNT && p.outC) p.outC[base + i] = s_c[i];
+    }
+}
+
+// ---- host side: one two-way pass ----------------------------------------------------------
+struct DevSet {
+    uint64_t* k = nullptr;
+    uint32_t* t = nullptr;
+    uint32_t* c = nullptr;
+    size_t n = 0;
+};
+
+constexpr size_t setop_smem(bool tax, bool cnt) {
+    return (size_t)(SO_TILE + 8) * 8 + (tax ? (size_t)(SO_TILE + 20) * 4 : 0) + (cnt ? (size_t)(SO_TILE + 20) * 4 : 0);
+}
+
+template <int OP, bool TAX, bool CNT>
+int launch_setop_v(ukm_ctx* ctx, const SetopArgs& a) {
+    constexpr size_t smem = setop_smem(TAX, CNT);
+    auto kern = setop_kernel<OP, TAX, CNT>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<a.num_tiles, SO_THREADS, smem, ctx->stream>>>(a);
+    UKM_CUDA(ctx, cudaGetLastError());
+    return UKM_OK;
+}
+
+template <int OP>
+int launch_setop(ukm_ctx* ctx, bool tax, bool cnt, const SetopArgs& a) {
+    if (tax && cnt) return launch_setop_v<OP, true, true>(ctx, a);
+    if (tax) return launch_setop_v<OP, true, false>(ctx, a);
+    if (cnt) return launch_setop_v<OP, false, true>(ctx, a);
+    return launch_setop_v<OP, false, false>(ctx, a);
+}
+
+const char* op_name(int op, bool tax) {
+    switch (op) {
+        case OP_INTER: return tax ? "setop_inter_tax" : "setop_inter";
+        case OP_DIFF: return tax ? "setop_diff_tax" : "setop_diff";
+        case OP_UNION: return tax ? "setop_union_tax" : "setop_union";
+        default: return tax ? "setop_merge_tax" : "setop_merge";
+    }
+}
+
+// out buffers must hold: INTER min(nA,nB); DIFF nA; UNION/MERGE nA+nB.  *n_out gets the count
+// (host value, after a stream sync).
+int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, bool cnt, unsigned flags, uint32_t threshold,
+           DevSet* out) {
+    const long long nA = (long long)A.n, nB = (long long)B.n;
+    const long long total = nA + nB;
+    if (total == 0) {
+        out->n = 0;
+        return UKM_OK;
+    }
+    const int num_tiles = (int)((total + SO_TILE - 1) / SO_TILE);
+    ukm_tmp tmp(ctx);
+    long long* d_part = nullptr;
+    uint64_t* d_status = nullptr;
+    uint32_t* d_counter = nullptr;
+    unsigned long long* d_total = nullptr;
+    UKM_TRY(tmp.alloc(&d_part, (size_t)2 * (num_tiles + 1)));
+    UKM_TRY(tmp.alloc(&d_status, (size_t)num_tiles + 4));
+    // d_counter and d_total live in the tail of the status allocation (zeroed together)
+    d_counter = reinterpret_cast<uint32_t*>(d_status + num_tiles);
+    d_total = reinterpret_cast<unsigned long long*>(d_status + num_tiles + 1);
+    UKM_CUDA(ctx, cudaMemsetAsync(d_status, 0, ((size_t)num_tiles + 4) * sizeof(uint64_t), ctx->stream));
+
+    {
+        ukm_stat_scope st(ctx, op_name(op, tax), (double)total * (tax ? 12.0 : 8.0));
+        setop_partition_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(A.k, nA, B.k, nB, num_tiles, op != OP_MERGE,
+                                                                                     d_part, ctx->d_err);
+        UKM_CUDA(ctx, cudaGetLastError());
+        SetopArgs a;
+        a.A = A.k; a.tA = A.t; a.cA = A.c; a.nA = nA;
+        a.B = B.k; a.tB = B.t; a.cB = B.c; a.nB = nB;
+        a.part = d_part;
+        a.outK = out->k; a.outT = out->t; a.outC = out->c;
+        a.status = d_status; a.tile_counter = d_counter; a.total_out = d_total;
+        a.num_tiles = num_tiles;
+        a.flags = flags;
+        a.threshold = threshold;
+        a.tax = ukm_taxdev(ctx);
+        a.err = ctx->d_err;
+        int r;
+        switch (op) {
+            case OP_INTER: r = launch_setop<OP_INTER>(ctx, tax, false, a); break;
+            case OP_DIFF: r = launch_setop<OP_DIFF>(ctx, tax, false, a); break;
+            case OP_UNION: r = launch_setop<OP_UNION>(ctx, tax, cnt, a); break;
+            default: r = launch_setop<OP_MERGE>(ctx, tax, false, a); break;
+        }
+        UKM_TRY(r);
+    }
+    UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->n = (size_t)ctx->h_scratch[0];
+    // algorithmic bytes = inputs read once + output written once
+    if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes += (double)out->n * (tax ? 12.0 : 8.0);
+    return UKM_OK;
+}
+
+int alloc_set(ukm_tmp& tmp, DevSet* s, size_t cap, bool tax, bool cnt) {
+    UKM_TRY(tmp.alloc(&s->k, cap + 2));
+    if (tax) UKM_TRY(tmp.alloc(&s->t, cap + 4));
+    if (cnt) UKM_TRY(tmp.alloc(&s->c, cap + 4));
+    s->n = 0;
+    return UKM_OK;
+}
+void free_set(ukm_tmp& tmp, DevSet* s) {
+    if (s->k) tmp.free_now(s->k);
+    if (s->t) tmp.free_now(s->t);
+    if (s->c) tmp.free_now(s->c);
+    *s = DevSet();
+}
+
+int stage_set(ukm_ctx* ctx, ukm_tmp& tmp, const ukm_span* in, bool tax, DevSet* s, bool* owned) {
+    ukm_dspan d;
+    size_t before = tmp.ptrs.size();
+    UKM_TRY(ukm_stage_in(ctx, tmp, in, tax, &d));
+    *owned = tmp.ptrs.size() != before;  // something was allocated for this span
+    s->k = d.keys;
+    s->t = d.taxids;
+    s->c = nullptr;
+    s->n = d.n;
+    return UKM_OK;
+}
+// free whatever stage_set allocated for this span (device spans are left alone)
+void unstage_set(ukm_tmp& tmp, const ukm_span* in, DevSet* s) {
+    if (in->where != UKM_DEVICE) {
+        if (s->k) tmp.free_now(s->k);
+        if (s->t) tmp.free_now(s->t);
+    } else if (s->t && s->t != in->taxids) {
+        tmp.free_now(s->t);
+    }
+    *s = DevSet();
+}
+
+int check_args(ukm_ctx* ctx, const ukm_span* in, int n_in, ukm_span* out, const char* what) {
+    if (!ctx) return UKM_E_ARG;
+    if (!in || n_in < 1 || !out) return ukm_fail(ctx, UKM_E_ARG, "%s: need at least one input span and an output span", what);
+    for (int i = 0; i < n_in; ++i)
+        if (in[i].n > ((size_t)1 << 40)) return ukm_fail(ctx, UKM_E_ARG, "%s: input %d too large", what, i);
+    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return UKM_OK;
+}
+
+int need_tax(ukm_ctx* ctx, unsigned flags, const char* what) {
+    if ((flags & (UKM_F_TAXID | UKM_F_MIX_TAXID)) && !ctx->tax.parent)
+        return ukm_fail(ctx, UKM_E_NO_TAXONOMY, "%s: taxids requested but no taxonomy loaded (ukm_set_taxonomy)", what);
+    return UKM_OK;
+}
+
+// running op in file order: cur = in[0]; cur = cur OP in[i]   (inter.go / diff.go iteration)
+int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags, ukm_span* out, const char* what) {
+    const bool tax = (flags & (UKM_F_TAXID | UKM_F_MIX_TAXID)) != 0;
+    ukm_tmp tmp(ctx);
+    DevSet cur, nxt, F;
+    bool owned;
+    UKM_TRY(stage_set(ctx, tmp, &in[0], tax, &cur, &owned));
+    bool cur_is_input = true;  // cur aliases the staged in[0]
+    const size_t cap = in[0].n;
+    DevSet bufs[2];
+    int which = 0;
+    for (int i = 1; i < n_in; ++i) {
+        if (op == OP_INTER) {
+            if (cur.n == 0 && cur_is_input) return ukm_fail(ctx, UKM_E_PANIC, "%s: first input is empty (inter.go:208 panics)", what);
+            if (in[i].n == 0) break;  // inter.go:211-215: flagBreak keeps the current set (quirk B-3)
+        }
+        if (op == OP_DIFF && in[i].n == 0) continue;
+        if (cur.n == 0) break;
+        UKM_TRY(stage_set(ctx, tmp, &in[i], tax, &F, &owned));
+        if (op == OP_DIFF && !in[i].sorted) {
+            // diff.go:341-367 handles an unsorted subject through a map; here: sort a private copy,
+            // then drop duplicate codes (a map delete is idempotent)
+            DevSet S;
+            UKM_TRY(alloc_set(tmp, &S, F.n, tax, false));
+            UKM_CUDA(ctx, cudaMemcpyAsync(S.k, F.k, F.n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (tax) UKM_CUDA(ctx, cudaMemcpyAsync(S.t, F.t, F.n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            unstage_set(tmp, &in[i], &F);
+            UKM_TRY(ukm_dev_sort(ctx, S.k, tax ? S.t : nullptr, S.n = in[i].n, 64));
+            DevSet U;
+            UKM_TRY(alloc_set(tmp, &U, S.n, tax, false));
+            size_t nu = 0;
+            UKM_TRY(ukm_dev_fold(ctx, UKM_FOLD_UNIQUE, S.k, S.t, S.n, tax, U.k, U.t, &nu));
+            // taxid of a deduplicated subject code: LCA over its occurrences
+            U.n = nu;
+            free_set(tmp, &S);
+            F = U;
+            owned = true;
+            if (bufs[which].k == nullptr) UKM_TRY(alloc_set(tmp, &bufs[which], cap, tax, false));
+            nxt = bufs[which];
+            UKM_TRY(setop2(ctx, op, cur, F, tax, false, flags, 0, &nxt));
+            free_set(tmp, &F);
+        } else {
+            if (bufs[which].k == nullptr) UKM_TRY(alloc_set(tmp, &bufs[which], cap, tax, false));
+            nxt = bufs[which];
+            UKM_TRY(setop2(ctx, op, cur, F, tax, false, flags, 0, &nxt));
+            unstage_set(tmp, &in[i], &F);
+        }
+        if (cur_is_input) {
+            unstage_set(tmp, &in[0], &cur);
+            cur_is_input = false;
+        }
+        bufs[which].n = nxt.n;
+        cur = nxt;
+        which ^= 1;
+    }
+    UKM_TRY(ukm_check_dev_error(ctx, what));
+    return ukm_deliver(ctx, cur.k, tax ? cur.t : nullptr, cur.n, out);
+}
+
+// balanced tree of two-way passes (union, common, merge)
+int run_tree(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags, bool cnt, uint32_t threshold, int fold_mode,
+             ukm_span* out, const char* what) {
+    const bool tax = (flags & UKM_F_TAXID) != 0;
+    ukm_tmp tmp(ctx);
+    std::vector<DevSet> level(n_in);
+    std::vector<int> src(n_in);  // index into `in` while the set is still a staged input, else -1
+    for (int i = 0; i < n_in; ++i) {
+        bool owned;
+        UKM_TRY(stage_set(ctx, tmp, &in[i], tax, &level[i], &owned));
+        src[i] = i;
+    }
+    // a single input still goes through one pass against an empty set so thresholds apply
+    if (level.size() == 1 && cnt) {
+        level.push_back(DevSet());
+        src.push_back(-2);
+    }
+    while (level.size() > 1) {
+        std::vector<DevSet> next;
+        std::vector<int> nsrc;
+        const bool last = level.size() == 2;
+        for (size_t i = 0; i + 1 < level.size(); i += 2) {
+            DevSet o;
+            UKM_TRY(alloc_set(tmp, &o, level[i].n + level[i + 1].n, tax, cnt));
+            UKM_TRY(setop2(ctx, op, level[i], level[i + 1], tax, cnt, flags, last ? threshold : 0, &o));
+            for (size_t j = i; j < i + 2; ++j) {
+                if (src[j] >= 0) unstage_set(tmp, &in[src[j]], &level[j]);
+                else if (src[j] == -1) free_set(tmp, &level[j]);
+            }
+            next.push_back(o);
+            nsrc.push_back(-1);
+        }
+        if (level.size() & 1) {
+            next.push_back(level.back());
+            nsrc.push_back(src.back());
+        }
+        level.swap(next);
+        src.swap(nsrc);
+    }
+    UKM_TRY(ukm_check_dev_error(ctx, what));
+    DevSet r = level[0];
+    if (fold_mode != UKM_FOLD_PLAIN) {
+        DevSet f;
+        UKM_TRY(alloc_set(tmp, &f, r.n + 2, tax, false));
+        size_t nf = 0;
+        UKM_TRY(ukm_dev_fold(ctx, fold_mode, r.k, r.t, r.n, tax, f.k, f.t, &nf));
+        f.n = nf;
+        r = f;
+    }
+    return ukm_deliver(ctx, r.k, tax ? r.t : nullptr, r.n, out);
+}
+
+}  // namespace
+
+extern "C" int ukm_inter(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_span* out) {
+    UKM_TRY(check_args(ctx, in, n_in, out, "ukm_inter"));
+    UKM_TRY(need_tax(ctx, flags & ~UKM_F_MIX_TAXID, "ukm_inter"));
+    return run_chain(ctx, OP_INTER, in, n_in, flags, out, "ukm_inter");
+}
+
+extern "C" int ukm_diff(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_span* out) {
+    UKM_TRY(check_args(ctx, in, n_in, out, "ukm_diff"));
+    if ((flags & UKM_F_COMPARE_TAXID) && (flags & UKM_F_TAXID)) UKM_TRY(need_tax(ctx, flags, "ukm_diff"));
+    return run_chain(ctx, OP_DIFF, in, n_in, flags & ~UKM_F_MIX_TAXID, out, "ukm_diff");
+}
+
+extern "C" int ukm_union(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_span* out) {
+    UKM_TRY(check_args(ctx, in, n_in, out, "ukm_union"));
+    UKM_TRY(need_tax(ctx, flags & UKM_F_TAXID, "ukm_union"));
+    return run_tree(ctx, OP_UNION, in, n_in, flags & UKM_F_TAXID, false, 0, UKM_FOLD_PLAIN, out, "ukm_union");
+}
+
+extern "C" int ukm_common(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, uint16_t threshold, ukm_span* out) {
+    UKM_TRY(check_args(ctx, in, n_in, out, "ukm_common"));
+    UKM_TRY(need_tax(ctx, flags & UKM_F_TAXID, "ukm_common"));
+    return run_tree(ctx, OP_UNION, in, n_in, flags & UKM_F_TAXID, true, threshold, UKM_FOLD_PLAIN, out, "ukm_common");
+}
+
+extern "C" int ukm_merge_sorted(ukm_ctx* ctx, int mode, const ukm_span* in, int n_in, unsigned flags, ukm_span* out) {
+    UKM_TRY(check_args(ctx, in, n_in, out, "ukm_merge_sorted"));
+    if (mode < UKM_FOLD_PLAIN || mode > UKM_FOLD_REPEATED_CHUNK) return ukm_fail(ctx, UKM_E_ARG, "ukm_merge_sorted: bad mode");
+    if (mode != UKM_FOLD_PLAIN) UKM_TRY(need_tax(ctx, flags & UKM_F_TAXID, "ukm_merge_sorted"));
+    return run_tree(ctx, OP_MERGE, in, n_in, flags & UKM_F_TAXID, false, 0, mode, out, "ukm_merge_sorted");
+}
