@@ -1,0 +1,112 @@
+"""Key-range sharding of the set operations across the GPUs of one box.
+
+One process per GPU (torch.distributed; NCCL on GPUs, gloo in the CPU tests).  All six
+operations are key-local -- the result for key x depends only on the occurrences of x --
+so the key space is cut into G contiguous ranges, rank r receives every input file's
+slice in its range with ONE grouped all-to-all-v (batched isend/irecv = one
+ncclGroupStart/End), runs the single-GPU operation on its bucket, and the global result is
+the concatenation of the per-rank outputs in rank order (already globally sorted).
+
+For sorted inputs the partition is G-1 binary searches per file (ukm_partition_sorted) and
+every payload is a contiguous slice: no scatter kernel, no second collective.
+
+`backend` is whatever runs the local pieces: unikmer_b200.Engine on a GPU.  (The gloo
+tests pass a stand-in so the exchange plan can be checked on CPU.)
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def equal_width_splitters(world: int, key_bits: int = 62) -> np.ndarray:
+    """G-1 splitters cutting [0, 2^key_bits) into equal-width ranges (uniform keys: k-mer codes of
+    random sequence, hashes).  Range r = [s[r-1], s[r])."""
+    return np.array([((i << key_bits) // world) for i in range(1, world)], dtype=np.uint64)
+
+
+def owner_of_file(f: int, world: int) -> int:
+    """Initial placement: file f lives on rank f mod G (files arrive from different readers)."""
+    return f % world
+
+
+class KeyRangeExchange:
+    def __init__(self, backend, rank: int, world: int, group=None):
+        self.backend = backend
+        self.rank = rank
+        self.world = world
+        self.group = group
+
+    def plan(self, local_files: Dict[int, torch.Tensor], n_files: int, splitters: np.ndarray):
+        """Binary-search every local file at the splitters and share the slice sizes.
+        Returns (offsets per local file, counts[f][r] = elements of file f in range r, for ALL files)."""
+        G = self.world
+        offsets = {}
+        counts = torch.zeros(n_files, G, dtype=torch.int64)
+        for f, t in local_files.items():
+            off = np.asarray(self.backend.partition_sorted(t, splitters), dtype=np.int64)
+            assert len(off) == G + 1 and off[0] == 0 and off[-1] == t.shape[0]
+            offsets[f] = off
+            counts[f] = torch.from_numpy(np.diff(off))
+        if G > 1:
+            dev = next(iter(local_files.values())).device if local_files else torch.device("cpu")
+            c = counts.to(dev)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM, group=self.group)  # every file has exactly one owner
+            counts = c.cpu()
+        return offsets, counts
+
+    def exchange(self, local_files: Dict[int, torch.Tensor], n_files: int, splitters: np.ndarray) -> List[torch.Tensor]:
+        """One all-to-all-v.  Returns, for every file id in order, this rank's key-range slice."""
+        G, me = self.world, self.rank
+        offsets, counts = self.plan(local_files, n_files, splitters)
+        out: List[torch.Tensor] = [None] * n_files  # type: ignore
+        ops = []
+        for f in range(n_files):
+            o = owner_of_file(f, G)
+            if o == me:
+                t, off = local_files[f], offsets[f]
+                out[f] = t[off[me]:off[me + 1]]  # own slice: a view, no copy
+                for r in range(G):
+                    if r != me and off[r + 1] > off[r]:
+                        ops.append(dist.P2POp(dist.isend, t[off[r]:off[r + 1]], r, group=self.group))
+            else:
+                n = int(counts[f, me])
+                ref = next(iter(local_files.values())) if local_files else None
+                buf = torch.empty(n, dtype=ref.dtype if ref is not None else torch.int64,
+                                  device=ref.device if ref is not None else "cpu")
+                out[f] = buf
+                if n:
+                    ops.append(dist.P2POp(dist.irecv, buf, o, group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return out
+
+    @staticmethod
+    def exchanged_bytes(counts: torch.Tensor, world: int) -> int:
+        """Bytes that cross NVLink in one exchange (everything except the owners' own slices)."""
+        total = int(counts.sum()) * 8
+        own = sum(int(counts[f, owner_of_file(f, world)]) for f in range(counts.shape[0])) * 8
+        return total - own
+
+
+def gather_rank_order(piece: torch.Tensor, rank: int, world: int, group=None) -> torch.Tensor:
+    """Concatenate per-rank outputs in rank order on every rank (tests / small results only)."""
+    if world == 1:
+        return piece
+    n = torch.tensor([piece.shape[0]], dtype=torch.int64, device=piece.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    bufs = [torch.empty(int(s.item()), dtype=piece.dtype, device=piece.device) for s in sizes]
+    dist.all_gather(bufs, piece.contiguous(), group=group) if len(set(int(s.item()) for s in sizes)) == 1 else _uneven_all_gather(bufs, piece, rank, world, group)
+    return torch.cat(bufs)
+
+
+def _uneven_all_gather(bufs: Sequence[torch.Tensor], piece: torch.Tensor, rank: int, world: int, group=None):
+    for r in range(world):
+        if r == rank:
+            bufs[r].copy_(piece)
+        dist.broadcast(bufs[r], src=r, group=group)
