@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark: sorted uint64 k-mers/sec for union / inter / diff.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], "C3" in SURVEY.md 8d): 8 sorted duplicate-free files of
+~5e8 k=31 k-mers each -- universe U(j; 1e9, S=3), file f holds U_j iff bit f of sm64(4+j).
+One STEP = `inter` + `diff` + `union` over the 8 files (each op consumes all ~4e9 input
+k-mers); value = (3 * sum |F_i|) / step time, inputs resident in HBM.
+
+N > 1 (strong scaling: same total work): file f starts on rank f mod N; every step does one
+grouped NCCL all-to-all-v by key range (unikmer_b200/dist.py) and then the three operations
+on each rank's bucket; results stay sharded in rank order.
+
+--impl reference: the reference's CPU algorithms for the same path (hash-map union,
+two-pointer inter/diff; oracle/oracle.c -- the Go reference cannot be built in this image)
+on a bounded sample of the same workload, on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S_SEED, T_SEED = 3, 4
+N_FILES = 8
+METRIC = "sorted_uint64_kmers_per_sec_union_inter_diff"
+UNIT = "k-mers/s"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        top = sorted(sm)[len(sm) // 2:] if sm else []  # samples under load = upper half
+        return {"sm_mhz": statistics.median(top) if top else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores, bounded sample
+# ---------------------------------------------------------------------------------------
+def cpu_pass(universe: int, threads: int):
+    """One inter + diff + union over the 8 files of a `universe`-sized sample, reference algorithms."""
+    import oracle
+    files = [oracle.member_file(0, universe, universe, S_SEED, T_SEED, f) for f in range(N_FILES)]
+    total = sum(len(f) for f in files)
+    t0 = time.perf_counter()
+    i, _ = oracle.inter(files)
+    t1 = time.perf_counter()
+    d, _ = oracle.diff(files, threads=threads)
+    t2 = time.perf_counter()
+    u, _ = oracle.union(files, threads=threads)
+    t3 = time.perf_counter()
+    return total, (t1 - t0, t2 - t1, t3 - t2), (len(i), len(d), len(u))
+
+
+def cpu_baseline(sample_universe: int):
+    threads = os.cpu_count() or 1
+    total, (ti, td, tu), sizes = cpu_pass(sample_universe, threads)
+    secs = ti + td + tu
+    return {"value": 3 * total / secs, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"C3 scaled to universe {sample_universe:.0e} (8 files x ~{sample_universe // 2:.1e} k-mers): one inter+diff+union pass, "
+                      f"{secs:.1f} s (inter {ti:.2f} s, diff {td:.2f} s, union {tu:.2f} s); C restatement of the Go algorithms "
+                      f"(hash-map union, two-pointer inter/diff; single goroutine each, the sort in union/diff uses {threads} threads)",
+            "per_op_kmers_per_s": {"inter": total / ti, "diff": total / td, "union": total / tu}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    uni = args.ref_universe
+    vals, last = [], None
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        total, ts, sizes = cpu_pass(uni, os.cpu_count() or 1)
+        dt = sum(ts)
+        if it >= args.warmup:
+            vals.append((3 * total / dt, dt))
+        last = (total, ts, sizes)
+    value = statistics.mean(v for v, _ in vals)
+    ms = 1e3 * statistics.mean(d for _, d in vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"C3 sample: inter+diff+union over 8 sorted files, universe {uni:.0e} (~{uni // 2:.1e} k-mers per file), k=31",
+                   "note": "Go reference cannot be built here (no Go toolchain, un-vendored modules): C restatement of its algorithms (oracle/oracle.c)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                         "sample": f"universe {uni:.0e}; per step inter {last[1][0]:.2f} s, diff {last[1][1]:.2f} s, union {last[1][2]:.2f} s"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--universe", type=float, default=1e9, help="universe size N (files hold ~N/2 k-mers each)")
+    ap.add_argument("--ref-universe", type=float, default=4e7, help="sample universe for the CPU arm")
+    ap.add_argument("--cpu-universe", type=float, default=2e7, help="sample universe for the cpu_baseline object")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--detail", action="store_true", help="print a per-kernel table to stderr")
+    args = ap.parse_args()
+    args.universe, args.ref_universe, args.cpu_universe = int(args.universe), int(args.ref_universe), int(args.cpu_universe)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from unikmer_b200 import Engine
+    from unikmer_b200.dist import KeyRangeExchange, equal_width_splitters, owner_of_file
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    eng = Engine(local)
+    stream = torch.cuda.Stream(device=dev)
+    eng.use_stream(stream.cuda_stream)
+    U = args.universe
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        # ---- inputs: generated on the device, resident in HBM before anything is timed ----
+        local_files = {}
+        for f in range(N_FILES):
+            if owner_of_file(f, world) == rank:
+                local_files[f] = eng.synth_member_file(0, U, U, S_SEED, T_SEED, f).clone()
+        torch.cuda.synchronize()
+        sizes = torch.zeros(N_FILES, dtype=torch.int64, device=dev)
+        for f, t in local_files.items():
+            sizes[f] = t.shape[0]
+        if world > 1:
+            dist.all_reduce(sizes)
+        total_in = int(sizes.sum().item())
+        splitters = equal_width_splitters(world, 62)
+        ex = KeyRangeExchange(eng, rank, world)
+
+        def step():
+            if world > 1:
+                files = ex.exchange(local_files, N_FILES, splitters)
+            else:
+                files = [local_files[f] for f in range(N_FILES)]
+            i, _ = eng.inter(files)
+            d, _ = eng.diff(files)
+            u, _ = eng.union(files)
+            return i, d, u
+
+        for _ in range(args.warmup):
+            res = step()
+        del res
+        eng.stats_reset()
+        eng.stats_enable(True)
+        launches0 = eng.launch_count()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            res = step()
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+        ms_step = float(ms_total.item()) / args.steps
+        launches = eng.launch_count() - launches0
+        eng.stats_enable(False)
+        stats = eng.stats()
+        value = 3.0 * total_in / (ms_step * 1e-3)
+
+        # ---- result checks: cardinalities + an exact window against the oracle ----
+        inter, diff, union = res
+        n_out = torch.tensor([inter.shape[0], diff.shape[0], union.shape[0]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(n_out)
+        n_inter, n_diff, n_union = (int(x) for x in n_out.tolist())
+        check = {"n_inter": n_inter, "n_diff": n_diff, "n_union": n_union}
+        if rank == 0:
+            import oracle
+            w = 2_000_000  # j-window [0, w): keys below U(w) -- exact parity of that window
+            W = (1 << 62) // U
+            bound = w * W
+            ofiles = [oracle.member_file(0, w, U, S_SEED, T_SEED, f) for f in range(N_FILES)]
+            for name, got, exp in (("inter", inter, oracle.inter(ofiles)[0]), ("diff", diff, oracle.diff(ofiles)[0]),
+                                   ("union", union, oracle.union(ofiles)[0])):
+                g = got[: len(exp) + 8].cpu().numpy().view(np.uint64)
+                g = g[g < bound]
+                ok = len(g) == len(exp) and bool(np.array_equal(g, exp))
+                check[f"{name}_window_exact"] = ok
+                if not ok:
+                    raise SystemExit(f"bench self-check failed: {name} window differs from the oracle")
+
+        # ---- roofline of the dominant kernel family (setop_*), from CUDA events on the stream ----
+        peak, peak_src = hbm_peak()
+        so = {k: v for k, v in stats.items() if k.startswith("setop_")}
+        so_ms = sum(v["ms"] for v in so.values())
+        so_bytes = sum(v["algo_bytes"] for v in so.values())
+        so_launch = sum(v["launches"] for v in so.values())
+        achieved = so_bytes / (so_ms * 1e-3) / 1e9 if so_ms else 0.0
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "setop_ncu_traffic.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": "setop_kernel (two-way merge-path set op; inter/diff/union passes)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                    "traffic": traffic, "peak_source": peak_src, "launches": so_launch,
+                    "avg_launch_ms": so_ms / so_launch if so_launch else None,
+                    "algo_bytes_per_launch": so_bytes / so_launch if so_launch else None,
+                    "share_of_step": so_ms / (ms_step * args.steps) if ms_step else None}
+
+        # ---- e2e: same step through the C ABI with HOST buffers (pinned), H2D + D2H in the timed region ----
+        e2e = None
+        if not args.no_e2e:
+            hfiles = {f: torch.empty(t.shape[0], dtype=torch.int64, pin_memory=True) for f, t in local_files.items()}
+            for f, t in local_files.items():
+                hfiles[f].copy_(t)
+            torch.cuda.synchronize()
+            h2d = d2h = 0
+            if world == 1:
+                order = [hfiles[f] for f in range(N_FILES)]
+                local_files.clear()  # free the device copies: the e2e path starts from host memory
+                torch.cuda.empty_cache()
+                ho_i = torch.empty(order[0].shape[0], dtype=torch.int64, pin_memory=True)
+                ho_d = torch.empty(order[0].shape[0], dtype=torch.int64, pin_memory=True)
+                ho_u = torch.empty(min(total_in, U) + 16, dtype=torch.int64, pin_memory=True)
+
+                def e2e_step():
+                    a = eng.inter(order, out=ho_i)[0]
+                    b = eng.diff(order, out=ho_d)[0]
+                    c = eng.union(order, out=ho_u)[0]
+                    return a.shape[0], b.shape[0], c.shape[0]
+                h2d = 3 * total_in * 8
+            else:
+                def e2e_step():
+                    dl = {f: h.to(dev, non_blocking=True) for f, h in hfiles.items()}
+                    files = ex.exchange(dl, N_FILES, splitters)
+                    outs = [eng.inter(files)[0], eng.diff(files)[0], eng.union(files)[0]]
+                    host = [o.to("cpu", non_blocking=True) for o in outs]
+                    torch.cuda.current_stream().synchronize()
+                    return tuple(h.shape[0] for h in host)
+                h2d = total_in * 8
+            e2e_step()  # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            e0.record(stream)
+            for _ in range(args.e2e_steps):
+                ns = e2e_step()
+            e1.record(stream)
+            barrier()
+            wall = (time.perf_counter() - t0) / args.e2e_steps
+            wt = torch.tensor([wall], dtype=torch.float64, device=dev)
+            nt = torch.tensor(list(ns), dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+                dist.all_reduce(nt)
+            d2h = int(nt.sum().item()) * 8
+            assert nt.tolist() == [n_inter, n_diff, n_union], "e2e results differ from the device-resident run"
+            e2e = {"value": 3.0 * total_in / float(wt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * float(wt.item()), "steps": args.e2e_steps,
+                   "path": "C ABI (ukm_inter/ukm_diff/ukm_union) with pinned HOST spans in and out" if world == 1 else
+                           "pinned host -> H2D -> key-range exchange -> device ops -> D2H"}
+
+        cpu = None
+        if rank == 0 and not args.no_cpu:
+            cpu = cpu_baseline(args.cpu_universe)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": f"C3: inter+diff+union over 8 sorted duplicate-free files x ~{U // 2:.1e} k=31 uint64 k-mers "
+                                   f"(universe {U:.0e}, {total_in} k-mers in); each op reads all inputs",
+                       "inputs": "device-resident, 32 GB >> 126 MB L2 (no L2 flush needed)" if U >= 10**8 else "device-resident",
+                       "parallelism": f"key-range shards x{world}, one NCCL all-to-all-v per step" if world > 1 else "1 GPU",
+                       "kmers_per_step": 3 * total_in},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "check": check,
+            "per_kernel": {k: {"launches": v["launches"], "ms": round(v["ms"], 3),
+                               "GBps": round(v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] else None}
+                           for k, v in stats.items()},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

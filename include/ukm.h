@@ -106,6 +106,8 @@ void* ukm_alloc_device(ukm_ctx* ctx, size_t bytes);
 int ukm_free_device(ukm_ctx* ctx, void* p);
 int ukm_copy(ukm_ctx* ctx, void* dst, int dst_where, const void* src, int src_where, size_t bytes);
 
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+uint64_t ukm_launch_count(ukm_ctx* ctx);
 int ukm_stats_enable(ukm_ctx* ctx, int on);
 int ukm_stats_reset(ukm_ctx* ctx);
 int ukm_stats_get(ukm_ctx* ctx, ukm_kernel_stat* out, int cap, int* n);

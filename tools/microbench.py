@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Per-kernel micro-benchmarks on one B200 (not the headline bench): radix sort configs, pair sort,
+k-mer/ntHash generation, count pipeline, folds.  Prints one JSON line per measurement."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from unikmer_b200 import Engine  # noqa: E402
+
+
+def timed(stream, fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=float, default=1e9)
+    ap.add_argument("--what", default="sort,pairs,kmers,count,fold")
+    args = ap.parse_args()
+    n = int(args.n)
+    eng = Engine(0)
+    stream = torch.cuda.Stream()
+    eng.use_stream(stream.cuda_stream)
+    what = args.what.split(",")
+    with torch.cuda.stream(stream):
+        if "sort" in what:
+            src = eng.synth_random_keys(0, n, 2)
+            work = torch.empty_like(src)
+            for cfg in ("0", "1", "2", "3"):
+                os.environ["UKM_SORT_CFG"] = cfg
+
+                def run():
+                    work.copy_(src)
+                    eng.sort(work, key_bits=62)
+                copy_ms = timed(stream, lambda: work.copy_(src))
+                eng.stats_reset(); eng.stats_enable(True)
+                ms = timed(stream, run) - copy_ms
+                eng.stats_enable(False)
+                st = eng.stats()
+                ok = bool((work[1:] >= work[:-1]).all().item())
+                print(json.dumps({"bench": "sort_u64", "n": n, "cfg": cfg, "ms": ms, "keys_per_s": n / ms * 1e3,
+                                  "GBps_136B": 136 * n / ms / 1e6, "GBps_actual": (1 + 2 * 8) * 8 * n / ms / 1e6, "sorted": ok,
+                                  "kernels": {k: round(v["ms"] / max(v["launches"], 1), 3) for k, v in st.items()}}), flush=True)
+            os.environ.pop("UKM_SORT_CFG", None)
+            del src, work
+        if "pairs" in what:
+            m = n // 2
+            src = eng.synth_random_keys(0, m, 2)
+            vals = torch.arange(m, dtype=torch.int32, device="cuda")
+            wk, wv = torch.empty_like(src), torch.empty_like(vals)
+
+            def run():
+                wk.copy_(src); wv.copy_(vals)
+                eng.sort(wk, wv, key_bits=62)
+            copy_ms = timed(stream, lambda: (wk.copy_(src), wv.copy_(vals)))
+            ms = timed(stream, run) - copy_ms
+            print(json.dumps({"bench": "sort_pairs", "n": m, "ms": ms, "keys_per_s": m / ms * 1e3}), flush=True)
+            del src, vals, wk, wv
+        if "kmers" in what or "count" in what:
+            L = min(n, 10**9)
+            nrec = 10
+            bases = torch.cat([eng.synth_bases(r, 0, L // nrec, 5) for r in range(nrec)])
+            off = torch.arange(0, nrec + 1, dtype=torch.int64, device="cuda") * (L // nrec)
+            for hashed in (True, False):
+                if "kmers" in what:
+                    eng.stats_reset(); eng.stats_enable(True)
+                    ms = timed(stream, lambda: eng.kmers(bases, off, 31, canonical=True, hashed=hashed), reps=2)
+                    eng.stats_enable(False)
+                    st = eng.stats()
+                    kk = [v for k, v in st.items() if k.startswith("kmer_")][0]
+                    kms = kk["ms"] / kk["launches"]
+                    print(json.dumps({"bench": "kmers", "hashed": hashed, "bases": L, "call_ms": ms, "kernel_ms": kms,
+                                      "kernel_GBps": 9 * L / kms / 1e6, "kmers_per_s": L / kms * 1e3}), flush=True)
+            if "count" in what:
+                eng.stats_reset(); eng.stats_enable(True)
+                ms = timed(stream, lambda: eng.count(bases, off, 31, canonical=True, hashed=True), reps=1)
+                eng.stats_enable(False)
+                print(json.dumps({"bench": "count_k31_KH", "bases": L, "ms": ms, "kmers_per_s": L / ms * 1e3,
+                                  "kernels": {k: round(v["ms"], 2) for k, v in eng.stats().items()}}), flush=True)
+            del bases
+        if "fold" in what:
+            m = n // 2
+            keys = eng.synth_random_keys(0, m, 2)
+            eng.sort(keys, key_bits=62)
+            eng.stats_reset(); eng.stats_enable(True)
+            ms = timed(stream, lambda: eng.fold(1, keys), reps=2)
+            eng.stats_enable(False)
+            st = eng.stats()["fold"]
+            kms = st["ms"] / st["launches"]
+            print(json.dumps({"bench": "fold_unique", "n": m, "call_ms": ms, "kernel_ms": kms, "kernel_GBps": 16 * m / kms / 1e6}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,7 +18,7 @@ F_TAXID, F_MIX_TAXID, F_COMPARE_TAXID, F_CANONICAL, F_HASHED, F_CIRCULAR, F_SCAL
 SYMBOLS = [
     "ukm_create", "ukm_destroy", "ukm_last_error", "ukm_version", "ukm_set_stream", "ukm_get_stream", "ukm_sync",
     "ukm_alloc_pinned", "ukm_free_pinned", "ukm_alloc_device", "ukm_free_device", "ukm_copy",
-    "ukm_stats_enable", "ukm_stats_reset", "ukm_stats_get",
+    "ukm_launch_count", "ukm_stats_enable", "ukm_stats_reset", "ukm_stats_get",
     "ukm_set_taxonomy", "ukm_lca_batch",
     "ukm_sort_u64", "ukm_sort_pairs", "ukm_sort_codetaxid16",
     "ukm_fold_sorted", "ukm_merge_sorted", "ukm_union", "ukm_inter", "ukm_diff", "ukm_common",
@@ -65,7 +65,7 @@ def load():
         "ukm_alloc_pinned": ([sz], vp), "ukm_free_pinned": ([vp], None),
         "ukm_alloc_device": ([vp, sz], vp), "ukm_free_device": ([vp, vp], i),
         "ukm_copy": ([vp, vp, i, vp, i, sz], i),
-        "ukm_stats_enable": ([vp, i], i), "ukm_stats_reset": ([vp], i),
+        "ukm_launch_count": ([vp], u64), "ukm_stats_enable": ([vp, i], i), "ukm_stats_reset": ([vp], i),
         "ukm_stats_get": ([vp, C.POINTER(KernelStat), i, C.POINTER(i)], i),
         "ukm_set_taxonomy": ([vp, vp, sz, vp, vp, sz], i),
         "ukm_lca_batch": ([vp, vp, vp, sz, vp, i], i),

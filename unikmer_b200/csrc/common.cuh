@@ -46,6 +46,7 @@ struct ukm_ctx {
     // pinned scratch for small D2H results (counts)
     uint64_t* h_scratch = nullptr;  // pinned, 64 words
     // stats
+    uint64_t launches = 0;  // kernels launched by this context
     bool stats_on = false;
     std::map<std::string, ukm_stat_acc> stats;
     std::vector<ukm_pending_event> pending;
@@ -60,6 +61,13 @@ int ukm_fail(ukm_ctx* ctx, int code, const char* fmt, ...);
         if (_e != cudaSuccess)                                                                     \
             return ukm_fail((ctx), _e == cudaErrorMemoryAllocation ? UKM_E_NOMEM : UKM_E_CUDA,     \
                             "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));   \
+    } while (0)
+
+// after every kernel launch: count it (ukm_launch_count) and pick up launch errors
+#define UKM_LAUNCHED(ctx)                       \
+    do {                                        \
+        (ctx)->launches++;                      \
+        UKM_CUDA((ctx), cudaGetLastError());    \
     } while (0)
 
 #define UKM_TRY(expr)              \
@@ -90,13 +98,14 @@ struct ukm_tmp {
         return UKM_OK;
     }
     // give up ownership of p (it becomes the caller's)
-    void release(void* p) {
+    bool release(void* p) {
         for (auto& q : ptrs)
-            if (q == p) { q = ptrs.back(); ptrs.pop_back(); return; }
+            if (q == p) { q = ptrs.back(); ptrs.pop_back(); return true; }
+        return false;
     }
+    // frees p only if this holder owns it (never a caller's buffer)
     void free_now(void* p) {
-        release(p);
-        ukm_dev_free(ctx, p);
+        if (release(p)) ukm_dev_free(ctx, p);
     }
 };
 

@@ -181,6 +181,8 @@ static void drain_stats(ukm_ctx* ctx) {
     ctx->pending.clear();
 }
 
+extern "C" uint64_t ukm_launch_count(ukm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
 extern "C" int ukm_stats_enable(ukm_ctx* ctx, int on) {
     if (!ctx) return UKM_E_ARG;
     drain_stats(ctx);
@@ -244,7 +246,7 @@ int ukm_dev_fill_u32(ukm_ctx* ctx, uint32_t* d, uint32_t v, size_t n) {
         return UKM_OK;
     }
     fill_u32_kernel<<<ukm_grid_for(n, 256 * 8, ctx->sm_count), 256, 0, ctx->stream>>>(d, v, n);
-    UKM_CUDA(ctx, cudaGetLastError());
+    UKM_LAUNCHED(ctx);
     return UKM_OK;
 }
 

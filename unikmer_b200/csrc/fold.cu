@@ -119,7 +119,7 @@ int launch_fold(ukm_ctx* ctx, bool tax, int num_tiles, const uint64_t* k, const 
     else
         fold_kernel<MODE, false><<<num_tiles, FD_THREADS, 0, ctx->stream>>>(k, t, n, ok, ot, status, counter, total, num_tiles,
                                                                             ukm_taxdev(ctx), ctx->d_err);
-    UKM_CUDA(ctx, cudaGetLastError());
+    UKM_LAUNCHED(ctx);
     return UKM_OK;
 }
 
@@ -245,7 +245,7 @@ extern "C" int ukm_check_sorted_unique(ukm_ctx* ctx, const ukm_span* in) {
     ukm_dspan d;
     UKM_TRY(ukm_stage_in(ctx, tmp, in, false, &d));
     check_sorted_unique_kernel<<<ukm_grid_for(d.n, 256 * 8, ctx->sm_count), 256, 0, ctx->stream>>>(d.keys, d.n, ctx->d_err);
-    UKM_CUDA(ctx, cudaGetLastError());
+    UKM_LAUNCHED(ctx);
     return ukm_check_dev_error(ctx, "ukm_check_sorted_unique");
 }
 
@@ -276,7 +276,7 @@ extern "C" int ukm_partition_sorted(ukm_ctx* ctx, const ukm_span* in, const uint
     UKM_TRY(tmp.alloc(&d_off, (size_t)n_split));
     UKM_CUDA(ctx, cudaMemcpyAsync(d_split, splitters, (size_t)n_split * 8, cudaMemcpyHostToDevice, ctx->stream));
     partition_sorted_kernel<<<(n_split + 63) / 64, 64, 0, ctx->stream>>>(in->keys, in->n, d_split, n_split, d_off);
-    UKM_CUDA(ctx, cudaGetLastError());
+    UKM_LAUNCHED(ctx);
     UKM_CUDA(ctx, cudaMemcpyAsync(offsets + 1, d_off, (size_t)n_split * 8, cudaMemcpyDeviceToHost, ctx->stream));
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return UKM_OK;

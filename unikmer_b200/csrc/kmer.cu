@@ -246,7 +246,7 @@ int generate(ukm_ctx* ctx, ukm_tmp& tmp, const uint8_t* bases, const uint64_t* r
         ukm_stat_scope st(ctx, hashed ? "kmer_nthash" : "kmer_encode", (double)n_bases + 8.0 * (double)total);
         if (hashed) kmer_kernel<true><<<grid, KM_THREADS, 0, ctx->stream>>>(a);
         else kmer_kernel<false><<<grid, KM_THREADS, 0, ctx->stream>>>(a);
-        UKM_CUDA(ctx, cudaGetLastError());
+        UKM_LAUNCHED(ctx);
     }
     // pageable host sources must stay valid until the copies above ran
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

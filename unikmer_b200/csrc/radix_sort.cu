@@ -271,7 +271,7 @@ int launch_onesweep(ukm_ctx* ctx, const uint64_t* kin, uint64_t* kout, const uin
     UKM_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)num_tiles * RADIX * sizeof(uint32_t), ctx->stream));
     kern<<<num_tiles, THREADS, smem, ctx->stream>>>(kin, kout, vin, vout, n, num_tiles, shift, mask, bases_in, bases_out, status,
                                                     counter, ctx->d_err);
-    UKM_CUDA(ctx, cudaGetLastError());
+    UKM_LAUNCHED(ctx);
     return UKM_OK;
 }
 
@@ -347,9 +347,9 @@ int ukm_dev_sort(ukm_ctx* ctx, uint64_t* d_keys, uint32_t* d_vals, size_t n, int
     {
         ukm_stat_scope st(ctx, "radix_hist", 8.0 * (double)n);
         radix_hist_kernel<<<ctx->sm_count * 4, HIST_THREADS, 0, ctx->stream>>>(d_keys, n, plan, d_hist);
-        UKM_CUDA(ctx, cudaGetLastError());
+        UKM_LAUNCHED(ctx);
         radix_bases_kernel<<<plan.npass, RADIX, 0, ctx->stream>>>(d_hist, d_bases);
-        UKM_CUDA(ctx, cudaGetLastError());
+        UKM_LAUNCHED(ctx);
     }
 
     uint64_t *ksrc = d_keys, *kdst = d_tmpk;
@@ -435,10 +435,10 @@ extern "C" int ukm_sort_codetaxid16(ukm_ctx* ctx, void* aos16, size_t n, int key
     UKM_CUDA(ctx, cudaMemcpyAsync(d_aos, aos16, n * 16, cudaMemcpyHostToDevice, ctx->stream));
     int g = ukm_grid_for(n, 256 * 4, ctx->sm_count);
     aos16_split_kernel<<<g, 256, 0, ctx->stream>>>(d_aos, dk, dv, n);
-    UKM_CUDA(ctx, cudaGetLastError());
+    UKM_LAUNCHED(ctx);
     UKM_TRY(ukm_dev_sort(ctx, dk, dv, n, key_bits));
     aos16_join_kernel<<<g, 256, 0, ctx->stream>>>(d_aos, dk, dv, n);
-    UKM_CUDA(ctx, cudaGetLastError());
+    UKM_LAUNCHED(ctx);
     UKM_CUDA(ctx, cudaMemcpyAsync(aos16, d_aos, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
     return ukm_check_dev_error(ctx, "ukm_sort_codetaxid16");
 }

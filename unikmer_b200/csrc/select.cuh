@@ -66,7 +66,7 @@ int ukm_dev_select(ukm_ctx* ctx, Gen gen, size_t n, uint64_t* d_out, size_t* n_o
     {
         ukm_stat_scope st(ctx, stat_name, algo_bytes_in);
         select_kernel<Gen><<<num_tiles, SEL_THREADS, 0, ctx->stream>>>(gen, n, d_out, d_status, d_counter, d_total, num_tiles, ctx->d_err);
-        UKM_CUDA(ctx, cudaGetLastError());
+        UKM_LAUNCHED(ctx);
     }
     UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

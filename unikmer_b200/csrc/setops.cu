@@ -338,7 +338,7 @@ int launch_setop_v(ukm_ctx* ctx, const SetopArgs& a) {
         configured = true;
     }
     kern<<<a.num_tiles, SO_THREADS, smem, ctx->stream>>>(a);
-    UKM_CUDA(ctx, cudaGetLastError());
+    UKM_LAUNCHED(ctx);
     return UKM_OK;
 }
 
@@ -386,7 +386,7 @@ int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, boo
         ukm_stat_scope st(ctx, op_name(op, tax), (double)total * (tax ? 12.0 : 8.0));
         setop_partition_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(A.k, nA, B.k, nB, num_tiles, op != OP_MERGE,
                                                                                      d_part, ctx->d_err);
-        UKM_CUDA(ctx, cudaGetLastError());
+        UKM_LAUNCHED(ctx);
         SetopArgs a;
         a.A = A.k; a.tA = A.t; a.cA = A.c; a.nA = nA;
         a.B = B.k; a.tB = B.t; a.cB = B.c; a.nB = nB;
@@ -548,7 +548,16 @@ int run_tree(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags,
         const bool last = level.size() == 2;
         for (size_t i = 0; i + 1 < level.size(); i += 2) {
             DevSet o;
-            UKM_TRY(alloc_set(tmp, &o, level[i].n + level[i + 1].n, tax, cnt));
+            const size_t bound = level[i].n + level[i + 1].n;
+            if (last && fold_mode == UKM_FOLD_PLAIN && out->where == UKM_DEVICE && out->cap >= bound && out->keys &&
+                (!tax || out->taxids)) {
+                // final pass writes straight into the caller's device buffers (no extra copy)
+                o.k = out->keys;
+                o.t = tax ? out->taxids : nullptr;
+                if (cnt) UKM_TRY(tmp.alloc(&o.c, bound + 4));
+            } else {
+                UKM_TRY(alloc_set(tmp, &o, bound, tax, cnt));
+            }
             UKM_TRY(setop2(ctx, op, level[i], level[i + 1], tax, cnt, flags, last ? threshold : 0, &o));
             for (size_t j = i; j < i + 2; ++j) {
                 if (src[j] >= 0) unstage_set(tmp, &in[src[j]], &level[j]);

@@ -39,7 +39,7 @@ extern "C" int ukm_synth_random_keys(ukm_ctx* ctx, uint64_t i0, size_t count, ui
     if (!count) return UKM_OK;
     UKM_CUDA(ctx, cudaSetDevice(ctx->device));
     random_keys_kernel<<<ukm_grid_for(count, 256 * 8, ctx->sm_count), 256, 0, ctx->stream>>>(i0, count, seed, d_out);
-    UKM_CUDA(ctx, cudaGetLastError());
+    UKM_LAUNCHED(ctx);
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return UKM_OK;
 }
@@ -60,7 +60,7 @@ extern "C" int ukm_synth_bases(ukm_ctx* ctx, uint64_t r, uint64_t i0, size_t cou
     if (!count) return UKM_OK;
     UKM_CUDA(ctx, cudaSetDevice(ctx->device));
     synth_bases_kernel<<<ukm_grid_for(count, 256 * 8, ctx->sm_count), 256, 0, ctx->stream>>>(r, i0, count, S, d_out);
-    UKM_CUDA(ctx, cudaGetLastError());
+    UKM_LAUNCHED(ctx);
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return UKM_OK;
 }

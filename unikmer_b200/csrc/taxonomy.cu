@@ -89,7 +89,7 @@ extern "C" int ukm_lca_batch(ukm_ctx* ctx, const uint32_t* a, const uint32_t* b,
         db = tb;
     }
     lca_batch_kernel<<<ukm_grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ukm_taxdev(ctx), da, db, dout, n);
-    UKM_CUDA(ctx, cudaGetLastError());
+    UKM_LAUNCHED(ctx);
     if (where != UKM_DEVICE) UKM_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return UKM_OK;

@@ -83,6 +83,9 @@ class Engine:
     def sync(self):
         self._chk(self.lib.ukm_sync(self.ctx))
 
+    def launch_count(self) -> int:
+        return int(self.lib.ukm_launch_count(self.ctx))
+
     def stats_enable(self, on: bool = True):
         self._chk(self.lib.ukm_stats_enable(self.ctx, int(on)))
 
@@ -108,12 +111,13 @@ class Engine:
         sp = L.Span()
         if _is_torch(s.keys):
             k = s.keys.contiguous()
-            assert k.is_cuda and k.element_size() == 8, "device codes must be a 64-bit CUDA tensor"
+            assert k.element_size() == 8, "codes must be a 64-bit tensor"
             keep.append(k)
-            sp.keys, sp.n, sp.where = k.data_ptr(), k.shape[0], L.DEVICE
+            # CUDA tensor -> device span; CPU (pinned) tensor -> host span
+            sp.keys, sp.n, sp.where = k.data_ptr(), k.shape[0], (L.DEVICE if k.is_cuda else L.HOST_PINNED)
             if s.taxids is not None:
                 t = s.taxids.contiguous()
-                assert t.is_cuda and t.element_size() == 4 and t.shape[0] == k.shape[0]
+                assert t.element_size() == 4 and t.shape[0] == k.shape[0]
                 keep.append(t)
                 sp.taxids = t.data_ptr()
         else:
@@ -134,7 +138,7 @@ class Engine:
         sets = [_as_set(s) for s in sets]
         if not sets:
             raise ValueError("need at least one k-mer set")
-        dev = [_is_torch(s.keys) for s in sets]
+        dev = [_is_torch(s.keys) and s.keys.is_cuda for s in sets]
         if any(dev) and not all(dev):
             raise ValueError("all inputs must live in the same memory space")
         keep: list = []
@@ -143,9 +147,23 @@ class Engine:
             arr[i] = self._span_in(s, keep)
         return arr, keep, all(dev)
 
-    def _span_out(self, cap: int, want_taxids: bool, device: bool):
+    def _span_out(self, cap: int, want_taxids: bool, device: bool, out=None):
+        """Output span.  `out` = caller-provided (keys[, taxids]) buffers (e.g. pinned host memory)."""
         sp = L.Span()
         cap = max(int(cap), 1)
+        if out is not None:
+            k, t = (out if isinstance(out, tuple) else (out, None))
+            if _is_torch(k):
+                sp.keys, sp.where = k.data_ptr(), (L.DEVICE if k.is_cuda else L.HOST_PINNED)
+                if t is not None:
+                    sp.taxids = t.data_ptr()
+            else:
+                assert k.dtype == np.uint64 and k.flags.c_contiguous
+                sp.keys, sp.where = k.ctypes.data, L.HOST
+                if t is not None:
+                    sp.taxids = t.ctypes.data
+            sp.cap = int(k.shape[0])
+            return sp, k, t
         if device:
             import torch
             k = torch.empty(cap, dtype=torch.int64, device=f"cuda:{self.device}")
@@ -216,26 +234,26 @@ class Engine:
         return self._trim(out, k, t)
 
     # ---- set operations ---------------------------------------------------------------------
-    def union(self, sets: Sequence, has_taxid: bool = False):
+    def union(self, sets: Sequence, has_taxid: bool = False, out=None):
         """`unikmer union -s` (union.go:186-208, 260-305)."""
         arr, keep, dev = self._spans(sets)
-        out, k, t = self._span_out(sum(int(a.n) for a in arr), has_taxid, dev)
+        out, k, t = self._span_out(sum(int(a.n) for a in arr), has_taxid, dev, out)
         self._chk(self.lib.ukm_union(self.ctx, arr, len(arr), L.F_TAXID if has_taxid else 0, C.byref(out)))
         return self._trim(out, k, t)
 
-    def inter(self, sets: Sequence, has_taxid: bool = False, mix_taxid: bool = False):
+    def inter(self, sets: Sequence, has_taxid: bool = False, mix_taxid: bool = False, out=None):
         """`unikmer inter [--mix-taxid]` (inter.go:188-286), iterated in file order."""
         arr, keep, dev = self._spans(sets)
         flags = (L.F_TAXID if has_taxid else 0) | (L.F_MIX_TAXID if mix_taxid else 0)
-        out, k, t = self._span_out(int(arr[0].n), has_taxid or mix_taxid, dev)
+        out, k, t = self._span_out(int(arr[0].n), has_taxid or mix_taxid, dev, out)
         self._chk(self.lib.ukm_inter(self.ctx, arr, len(arr), flags, C.byref(out)))
         return self._trim(out, k, t)
 
-    def diff(self, sets: Sequence, has_taxid: bool = False, compare_taxid: bool = False):
+    def diff(self, sets: Sequence, has_taxid: bool = False, compare_taxid: bool = False, out=None):
         """`unikmer diff -s [-t]` (diff.go:136-146, 341-515, 566-594)."""
         arr, keep, dev = self._spans(sets)
         flags = (L.F_TAXID if has_taxid else 0) | (L.F_COMPARE_TAXID if compare_taxid else 0)
-        out, k, t = self._span_out(int(arr[0].n), has_taxid, dev)
+        out, k, t = self._span_out(int(arr[0].n), has_taxid, dev, out)
         self._chk(self.lib.ukm_diff(self.ctx, arr, len(arr), flags, C.byref(out)))
         return self._trim(out, k, t)
 
