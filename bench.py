@@ -227,6 +227,7 @@ def main():
             u, _ = eng.union(files)
             return i, d, u
 
+        res = None
         for _ in range(args.warmup):
             res = step()
         del res

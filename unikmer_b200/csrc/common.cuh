@@ -338,4 +338,73 @@ __device__ __forceinline__ uint64_t lookback_warp(uint64_t* status, int tile, ui
     return prefix;
 }
 
+// Block-wide variant: ALL threads of the CTA call it; NTHREADS predecessors are inspected per
+// round, so the window covers every concurrently resident tile in one or two L2 round trips
+// (a 32-wide window cannot keep up when ~600 tiles are in flight: measured 4x slowdown).
+// `sh` = shared scratch of 3*(NTHREADS/32) + 2 unsigned long long.  Returns the exclusive prefix
+// to every thread.  Contains __syncthreads.
+template <int NTHREADS>
+__device__ __forceinline__ uint64_t lookback_block(uint64_t* status, int tile, uint64_t aggregate, int* err,
+                                                   unsigned long long* sh) {
+    constexpr int NW = NTHREADS / 32;
+    const unsigned l = lane_id();
+    const int w = threadIdx.x >> 5;
+    if (tile == 0) {
+        if (threadIdx.x == 0) st_release_u64(&status[0], UKM_LB_INCLUSIVE | aggregate);
+        return 0;
+    }
+    if (threadIdx.x == 0) st_release_u64(&status[tile], UKM_LB_PARTIAL | aggregate);
+    unsigned long long* sh_sum = sh;            // [NW] sum of the values this warp may contribute
+    unsigned long long* sh_take = sh + NW;      // [NW] number of lanes taken (0..32)
+    unsigned long long* sh_state = sh + 2 * NW; // [NW] 0 = full window of partials, 1 = blocked by an empty word, 2 = hit an inclusive word
+    uint64_t prefix = 0;
+    int base = tile - 1;  // thread i inspects tile base - i
+    unsigned spins = 0;
+    while (true) {
+        const int j = base - (int)threadIdx.x;
+        const uint64_t word = (j >= 0) ? ld_acquire_u64(&status[j]) : UKM_LB_INCLUSIVE;
+        const unsigned flag = (unsigned)(word >> 62);
+        const unsigned empty = __ballot_sync(0xffffffffu, flag == 0);
+        const unsigned incl = __ballot_sync(0xffffffffu, flag == 2);
+        const unsigned fe = empty ? (unsigned)(__ffs(empty) - 1) : 32u;
+        const unsigned fi = incl ? (unsigned)(__ffs(incl) - 1) : 32u;
+        unsigned take, state;
+        if (fi < fe) { take = fi + 1; state = 2; }
+        else if (fe < 32u) { take = fe; state = 1; }
+        else { take = 32; state = 0; }
+        uint64_t v = (l < take) ? UKM_LB_VALUE(word) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (l == 0) {
+            sh_sum[w] = v;
+            sh_take[w] = take;
+            sh_state[w] = state;
+        }
+        __syncthreads();
+        unsigned consumed = 0, fin = 0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            if (fin == 0) {
+                prefix += sh_sum[q];
+                consumed += (unsigned)sh_take[q];
+                if (sh_state[q] != 0) fin = (unsigned)sh_state[q];
+            }
+        }
+        __syncthreads();
+        if (fin == 2) break;
+        base -= (int)consumed;
+        if (consumed == 0) {
+            if (++spins > UKM_WATCHDOG_SPINS) {
+                if (threadIdx.x == 0) atomicExch(err, (int)UKM_E_INTERNAL);
+                prefix = 0;
+                break;
+            }
+        } else {
+            spins = 0;
+        }
+    }
+    if (threadIdx.x == 0) st_release_u64(&status[tile], UKM_LB_INCLUSIVE | (prefix + aggregate));
+    return prefix;
+}
+
 #endif  // __CUDACC__

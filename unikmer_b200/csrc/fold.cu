@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(FD_THREADS)
     __shared__ uint32_t s_ot[TAX ? FD_TILE + 2 : 1];
     __shared__ unsigned s_scan[NW + 2];
     __shared__ int s_tile;
-    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned long long s_lb[3 * NW + 2];
 
     const int tid = threadIdx.x;
     if (tid == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
@@ -77,13 +77,6 @@ __global__ void __launch_bounds__(FD_THREADS)
     }
     unsigned tile_total;
     const unsigned off = block_excl_scan_u32<FD_THREADS>(cnt, s_scan, &tile_total);
-    if (tid < 32) {
-        unsigned long long prefix = lookback_warp(status, tile, tile_total, err);
-        if (tid == 0) {
-            s_prefix = prefix;
-            if (tile == num_tiles - 1) *total_out = prefix + tile_total;
-        }
-    }
     {
         unsigned o = off;
 #pragma unroll
@@ -102,8 +95,9 @@ __global__ void __launch_bounds__(FD_THREADS)
             }
         }
     }
+    const unsigned long long pre = lookback_block<FD_THREADS>(status, tile, tile_total, err, s_lb);
+    if (tid == 0 && tile == num_tiles - 1) *total_out = pre + tile_total;
     __syncthreads();
-    const unsigned long long pre = s_prefix;
     for (unsigned i = tid; i < tile_total; i += FD_THREADS) {
         outK[pre + i] = s_ok[i];
         if (TAX) outT[pre + i] = s_ot[i];

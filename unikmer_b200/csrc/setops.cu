@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
     __shared__ int s_part[SO_THREADS + 1];  // packed (a << 16 | b) thread starts
     __shared__ unsigned s_scan[NW + 2];
     __shared__ int s_tile;
-    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned long long s_lb[3 * NW + 2];
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -286,15 +286,6 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
     const unsigned cnt = (unsigned)__popc(emitmask);
     unsigned tile_total;
     const unsigned off = block_excl_scan_u32<SO_THREADS>(cnt, s_scan, &tile_total);
-    if (tid < 32) {
-        unsigned long long prefix;
-        if (OP == OP_MERGE) prefix = (unsigned long long)(a_lo + b_lo);
-        else prefix = lookback_warp(p.status, tile, tile_total, p.err);
-        if (tid == 0) {
-            s_prefix = prefix;
-            if (tile == p.num_tiles - 1) *p.total_out = prefix + tile_total;
-        }
-    }
     {
         unsigned o = off;
 #pragma unroll
@@ -307,8 +298,12 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
             }
         }
     }
+    unsigned long long prefix;
+    if (OP == OP_MERGE) prefix = (unsigned long long)(a_lo + b_lo);
+    else prefix = lookback_block<SO_THREADS>(p.status, tile, tile_total, p.err, s_lb);
+    if (tid == 0 && tile == p.num_tiles - 1) *p.total_out = prefix + tile_total;
     __syncthreads();
-    const unsigned long long base = s_prefix;
+    const unsigned long long base = prefix;
     for (unsigned i = tid; i < tile_total; i += SO_THREADS) {
         p.outK[base + i] = s_k[i];
         if (TAX) p.outT[base + i] = s_t[i];
