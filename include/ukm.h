@@ -22,9 +22,10 @@
  *    without PCIe traffic.
  *  - set operations require every input to be sorted ascending and duplicate-free
  *    (what `unikmer count -s` / `sort -u` write, and what inter.go:139, diff.go:115,
- *    common.go:166 demand via the header flag).  A violation is reported as
- *    UKM_E_NOT_SORTED_UNIQUE instead of reproducing the reference's
- *    duplicate-dependent quirks.
+ *    common.go:166 demand via the header flag).  With UKM_F_VALIDATE a violation is
+ *    reported as UKM_E_NOT_SORTED_UNIQUE (the reference's duplicate-dependent quirks,
+ *    SURVEY.md Appendix B-4, B-7, are not reproduced); without it the flag is trusted,
+ *    exactly like the reference trusts the file header.
  */
 #ifndef UKM_H
 #define UKM_H
@@ -69,6 +70,8 @@ typedef enum ukm_fold_mode {
 #define UKM_F_HASHED 16u       /* count -H: ntHash v1 instead of the 2-bit code */
 #define UKM_F_CIRCULAR 32u     /* count --circular */
 #define UKM_F_SCALED 64u       /* count -D: keep code <= max_hash (count.go:373) */
+#define UKM_F_VALIDATE 128u    /* set ops: verify every input is sorted + duplicate-free first (one extra read);
+                                  without it the header flag is trusted, as the reference does (inter.go:139) */
 
 /* One k-mer stream: what unik.Reader.ReadCodeWithTaxid yields for a file, as arrays.
  * Mirrors []uint64 / []CodeTaxid (kmers.go:24-46) in SoA form. */

@@ -90,9 +90,11 @@ def test_sort_u64_sizes(eng, n):
     same(got, np.sort(keys), f"sort n={n}")
 
 
+@pytest.mark.parametrize("match", ["any", "ballot"])
 @pytest.mark.parametrize("cfg", ["0", "1", "2", "3"])
-def test_sort_tile_configs(eng, cfg, monkeypatch):
+def test_sort_tile_configs(eng, cfg, match, monkeypatch):
     monkeypatch.setenv("UKM_SORT_CFG", cfg)
+    monkeypatch.setenv("UKM_SORT_MATCH", match)
     keys = rng(int(cfg)).integers(0, 2**64, 700_001, dtype=U64)
     got, _ = eng.sort(keys.copy(), key_bits=64)
     same(got, np.sort(keys), f"sort cfg={cfg}")
@@ -191,6 +193,45 @@ def member_files(N, nfiles, S=3, T=4):
     return [oracle.member_file(0, N, N, S, T, f) for f in range(nfiles)]
 
 
+@pytest.mark.parametrize("vt", ["11", "15", "19", "23"])
+@pytest.mark.parametrize("skew", ["0", "3"])
+def test_setop_kernel_variants(eng, vt, skew, monkeypatch):
+    """Every tile shape of the keys-only merge kernel, with and without the search path for skewed pairs."""
+    monkeypatch.setenv("UKM_SETOP_VT", vt)
+    monkeypatch.setenv("UKM_SETOP_SKEW", skew)
+    files = member_files(400_000, 8)
+    same(eng.inter(files)[0], oracle.inter(files)[0], "inter")
+    same(eng.diff(files)[0], oracle.diff(files)[0], "diff")
+    same(eng.union(files)[0], oracle.union(files)[0], "union")
+    chunks = [np.sort(rng(3).integers(0, 90_000, n).astype(U64)) for n in (120_000, 7, 55_555)]
+    same(eng.merge(chunks, oracle.FOLD_PLAIN)[0], oracle.merge_chunks(chunks, oracle.FOLD_PLAIN)[0], "merge")
+
+
+def test_search_path_skewed_pairs(eng, tax):
+    """|B| >> |A|: the look-up kernel (inter/diff after a few files), keys-only and with taxids."""
+    otax, n_tax = tax
+    r = rng(77)
+    big = np.unique(r.integers(0, 2**62, 3_000_000, dtype=U64))
+    for n_small in (1, 5, 1000, 100_000):
+        hit = r.choice(big, n_small // 2 + 1, replace=False)
+        miss = r.integers(0, 2**62, n_small, dtype=U64)
+        small = np.unique(np.concatenate([hit, miss, [big[0], big[-1]]]))
+        for files in ([small, big], [small, big, big[::3].copy()]):
+            same(eng.inter(files)[0], oracle.inter(files)[0], f"search inter {n_small}")
+            same(eng.diff(files)[0], oracle.diff(files)[0], f"search diff {n_small}")
+        ts, tb = r.integers(0, n_tax, len(small)).astype(np.uint32), r.integers(0, n_tax, len(big)).astype(np.uint32)
+        tf = [(small, ts), (big, tb)]
+        for kw in ({"has_taxid": True}, {"mix_taxid": True}):
+            ek, et = oracle.inter(tf, tax=otax, **kw)
+            gk, gt = eng.inter(tf, **kw)
+            same(gk, ek, f"search inter tax keys {kw}")
+            same(gt, et, f"search inter tax taxids {kw}")
+        ek, et = oracle.diff(tf, has_taxid=True, compare_taxid=True, tax=otax)
+        gk, gt = eng.diff(tf, has_taxid=True, compare_taxid=True)
+        same(gk, ek, "search diff -t keys")
+        same(gt, et, "search diff -t taxids")
+
+
 @pytest.mark.parametrize("N,nfiles", [(1000, 2), (20_000, 3), (300_000, 8), (2_000_000, 2), (1_500_000, 5)])
 def test_setops_no_taxid(eng, N, nfiles):
     files = member_files(N, nfiles)
@@ -260,9 +301,12 @@ def test_setops_reject_unsorted_or_duplicate_input(eng):
     bad = a.copy()
     bad[20_000] = bad[20_001]  # duplicate
     for files in ([bad, a], [a, bad]):
-        with pytest.raises(ub.UkmError) as ei:
-            eng.inter(files)
-        assert ei.value.status == ub.E_NOT_SORTED_UNIQUE
+        for op in (eng.inter, eng.diff, eng.union):
+            with pytest.raises(ub.UkmError) as ei:
+                op(files, validate=True)  # UKM_F_VALIDATE; without it the header flag is trusted (inter.go:139)
+            assert ei.value.status == ub.E_NOT_SORTED_UNIQUE
+    with pytest.raises(ub.UkmError):
+        eng.common([a, bad], 1, validate=True)
     assert eng.check_sorted_unique(a[np.concatenate([[True], a[1:] != a[:-1]])])
     assert not eng.check_sorted_unique(bad)
     # the context stays usable after an error

@@ -40,8 +40,9 @@ def main():
         if "sort" in what:
             src = eng.synth_random_keys(0, n, 2)
             work = torch.empty_like(src)
-            for cfg in ("0", "1", "2", "3"):
+            for cfg, match in [(c, m) for m in ("any", "ballot") for c in ("0", "1", "2", "3")]:
                 os.environ["UKM_SORT_CFG"] = cfg
+                os.environ["UKM_SORT_MATCH"] = match
 
                 def run():
                     work.copy_(src)
@@ -52,11 +53,30 @@ def main():
                 eng.stats_enable(False)
                 st = eng.stats()
                 ok = bool((work[1:] >= work[:-1]).all().item())
-                print(json.dumps({"bench": "sort_u64", "n": n, "cfg": cfg, "ms": ms, "keys_per_s": n / ms * 1e3,
+                print(json.dumps({"bench": "sort_u64", "n": n, "cfg": cfg, "match": match, "ms": ms, "keys_per_s": n / ms * 1e3,
                                   "GBps_136B": 136 * n / ms / 1e6, "GBps_actual": (1 + 2 * 8) * 8 * n / ms / 1e6, "sorted": ok,
                                   "kernels": {k: round(v["ms"] / max(v["launches"], 1), 3) for k, v in st.items()}}), flush=True)
             os.environ.pop("UKM_SORT_CFG", None)
+            os.environ.pop("UKM_SORT_MATCH", None)
             del src, work
+        if "setops" in what:
+            U = n
+            files = [eng.synth_member_file(0, U, U, 3, 4, f).clone() for f in range(8)]
+            tot = sum(int(f.shape[0]) for f in files)
+            for vt, skew in [("15", "0"), ("11", "3"), ("15", "3"), ("19", "3"), ("23", "3")]:
+                os.environ["UKM_SETOP_VT"], os.environ["UKM_SETOP_SKEW"] = vt, skew
+                res = {}
+                for name in ("inter", "diff", "union"):
+                    fn = getattr(eng, name)
+                    eng.stats_reset(); eng.stats_enable(True)
+                    ms = timed(stream, lambda: fn(files), reps=3)
+                    eng.stats_enable(False)
+                    st = eng.stats()
+                    res[name] = {"ms": round(ms, 3), "kmers_per_s": tot / ms * 1e3,
+                                 "launch_ms": [round(v["ms"] / 4, 3) for k, v in st.items() if k.startswith("setop")]}
+                print(json.dumps({"bench": "setops_C3", "universe": U, "vt": vt, "skew": skew, **res}), flush=True)
+            os.environ.pop("UKM_SETOP_VT", None); os.environ.pop("UKM_SETOP_SKEW", None)
+            del files
         if "pairs" in what:
             m = n // 2
             src = eng.synth_random_keys(0, m, 2)

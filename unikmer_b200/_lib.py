@@ -12,7 +12,7 @@ OK, E_ARG, E_CUDA, E_NOMEM, E_CAPACITY, E_NOT_SORTED_UNIQUE, E_ILLEGAL_BASE, E_N
     0, -1, -2, -3, -4, -5, -6, -7, -8, -9)
 HOST, HOST_PINNED, DEVICE = 0, 1, 2
 FOLD_PLAIN, FOLD_UNIQUE, FOLD_REPEATED_FINAL, FOLD_REPEATED_CHUNK = 0, 1, 2, 3
-F_TAXID, F_MIX_TAXID, F_COMPARE_TAXID, F_CANONICAL, F_HASHED, F_CIRCULAR, F_SCALED = 1, 2, 4, 8, 16, 32, 64
+F_TAXID, F_MIX_TAXID, F_COMPARE_TAXID, F_CANONICAL, F_HASHED, F_CIRCULAR, F_SCALED, F_VALIDATE = 1, 2, 4, 8, 16, 32, 64, 128
 
 # every symbol include/ukm.h declares (tests check that the library exports all of them)
 SYMBOLS = [

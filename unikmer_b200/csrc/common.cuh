@@ -137,6 +137,7 @@ int ukm_dev_sort(ukm_ctx* ctx, uint64_t* d_keys, uint32_t* d_vals, size_t n, int
 int ukm_dev_fold(ukm_ctx* ctx, int mode, const uint64_t* d_keys, const uint32_t* d_taxids, size_t n,
                  bool has_taxid, uint64_t* d_out_keys, uint32_t* d_out_taxids, size_t* n_out);
 int ukm_dev_fill_u32(ukm_ctx* ctx, uint32_t* d, uint32_t v, size_t n);
+int ukm_dev_check_sorted_unique(ukm_ctx* ctx, const uint64_t* d_keys, size_t n);  // sets the device error word
 
 static inline int ukm_grid_for(size_t work, int per_block, int sm_count, int max_per_sm = 32) {
     size_t g = (work + per_block - 1) / per_block;
@@ -186,7 +187,25 @@ __device__ __forceinline__ void st_stream_u64x2(ulonglong2* p, ulonglong2 v) {
     asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
 }
 
-// relaxed / acquire / release accesses for the decoupled look-back words
+// Look-back status words carry their whole payload in one 64-bit (or 32-bit) word, so relaxed
+// (L1-bypassing) accesses are enough; ld.acquire.gpu would cost an L1 invalidate (CCTL.IVALL) per poll.
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// acquire / release variants (kept for data-carrying hand-offs)
 __device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t* p) {
     uint64_t v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -293,16 +312,16 @@ __device__ __forceinline__ unsigned block_excl_scan_u32(unsigned v, unsigned* ws
 __device__ __forceinline__ uint64_t lookback_warp(uint64_t* status, int tile, uint64_t aggregate, int* err) {
     unsigned l = lane_id();
     if (tile == 0) {
-        if (l == 0) st_release_u64(&status[0], UKM_LB_INCLUSIVE | aggregate);
+        if (l == 0) st_relaxed_u64(&status[0], UKM_LB_INCLUSIVE | aggregate);
         return 0;
     }
-    if (l == 0) st_release_u64(&status[tile], UKM_LB_PARTIAL | aggregate);
+    if (l == 0) st_relaxed_u64(&status[tile], UKM_LB_PARTIAL | aggregate);
     uint64_t prefix = 0;
     int base = tile - 1;  // lane l inspects tile base - l
     unsigned spins = 0;
     while (true) {
         int j = base - (int)l;
-        uint64_t w = (j >= 0) ? ld_acquire_u64(&status[j]) : UKM_LB_INCLUSIVE;  // before tile 0: inclusive 0
+        uint64_t w = (j >= 0) ? ld_relaxed_u64(&status[j]) : UKM_LB_INCLUSIVE;  // before tile 0: inclusive 0
         unsigned flag = (unsigned)(w >> 62);
         unsigned empty = __ballot_sync(0xffffffffu, flag == 0);
         unsigned incl = __ballot_sync(0xffffffffu, flag == 2);
@@ -331,80 +350,22 @@ __device__ __forceinline__ uint64_t lookback_warp(uint64_t* status, int tile, ui
                 prefix = 0;
                 break;
             }
-            __nanosleep(20);
         }
     }
-    if (l == 0) st_release_u64(&status[tile], UKM_LB_INCLUSIVE | (prefix + aggregate));
+    if (l == 0) st_relaxed_u64(&status[tile], UKM_LB_INCLUSIVE | (prefix + aggregate));
     return prefix;
 }
 
-// Block-wide variant: ALL threads of the CTA call it; NTHREADS predecessors are inspected per
-// round, so the window covers every concurrently resident tile in one or two L2 round trips
-// (a 32-wide window cannot keep up when ~600 tiles are in flight: measured 4x slowdown).
-// `sh` = shared scratch of 3*(NTHREADS/32) + 2 unsigned long long.  Returns the exclusive prefix
-// to every thread.  Contains __syncthreads.
-template <int NTHREADS>
-__device__ __forceinline__ uint64_t lookback_block(uint64_t* status, int tile, uint64_t aggregate, int* err,
-                                                   unsigned long long* sh) {
-    constexpr int NW = NTHREADS / 32;
-    const unsigned l = lane_id();
-    const int w = threadIdx.x >> 5;
-    if (tile == 0) {
-        if (threadIdx.x == 0) st_release_u64(&status[0], UKM_LB_INCLUSIVE | aggregate);
-        return 0;
+// All threads call this after staging their outputs: warp 0 chains the tile total, the barrier
+// publishes both the prefix and the staged data.  `s_prefix` is one shared 64-bit word.
+__device__ __forceinline__ uint64_t tile_exclusive_prefix(uint64_t* status, int tile, uint64_t tile_total, int* err,
+                                                          unsigned long long* s_prefix) {
+    if (threadIdx.x < 32) {
+        uint64_t pre = lookback_warp(status, tile, tile_total, err);
+        if (threadIdx.x == 0) *s_prefix = pre;
     }
-    if (threadIdx.x == 0) st_release_u64(&status[tile], UKM_LB_PARTIAL | aggregate);
-    unsigned long long* sh_sum = sh;            // [NW] sum of the values this warp may contribute
-    unsigned long long* sh_take = sh + NW;      // [NW] number of lanes taken (0..32)
-    unsigned long long* sh_state = sh + 2 * NW; // [NW] 0 = full window of partials, 1 = blocked by an empty word, 2 = hit an inclusive word
-    uint64_t prefix = 0;
-    int base = tile - 1;  // thread i inspects tile base - i
-    unsigned spins = 0;
-    while (true) {
-        const int j = base - (int)threadIdx.x;
-        const uint64_t word = (j >= 0) ? ld_acquire_u64(&status[j]) : UKM_LB_INCLUSIVE;
-        const unsigned flag = (unsigned)(word >> 62);
-        const unsigned empty = __ballot_sync(0xffffffffu, flag == 0);
-        const unsigned incl = __ballot_sync(0xffffffffu, flag == 2);
-        const unsigned fe = empty ? (unsigned)(__ffs(empty) - 1) : 32u;
-        const unsigned fi = incl ? (unsigned)(__ffs(incl) - 1) : 32u;
-        unsigned take, state;
-        if (fi < fe) { take = fi + 1; state = 2; }
-        else if (fe < 32u) { take = fe; state = 1; }
-        else { take = 32; state = 0; }
-        uint64_t v = (l < take) ? UKM_LB_VALUE(word) : 0ull;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        if (l == 0) {
-            sh_sum[w] = v;
-            sh_take[w] = take;
-            sh_state[w] = state;
-        }
-        __syncthreads();
-        unsigned consumed = 0, fin = 0;
-#pragma unroll
-        for (int q = 0; q < NW; ++q) {
-            if (fin == 0) {
-                prefix += sh_sum[q];
-                consumed += (unsigned)sh_take[q];
-                if (sh_state[q] != 0) fin = (unsigned)sh_state[q];
-            }
-        }
-        __syncthreads();
-        if (fin == 2) break;
-        base -= (int)consumed;
-        if (consumed == 0) {
-            if (++spins > UKM_WATCHDOG_SPINS) {
-                if (threadIdx.x == 0) atomicExch(err, (int)UKM_E_INTERNAL);
-                prefix = 0;
-                break;
-            }
-        } else {
-            spins = 0;
-        }
-    }
-    if (threadIdx.x == 0) st_release_u64(&status[tile], UKM_LB_INCLUSIVE | (prefix + aggregate));
-    return prefix;
+    __syncthreads();
+    return *s_prefix;
 }
 
 #endif  // __CUDACC__

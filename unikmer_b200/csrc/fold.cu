@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(FD_THREADS)
     __shared__ uint32_t s_ot[TAX ? FD_TILE + 2 : 1];
     __shared__ unsigned s_scan[NW + 2];
     __shared__ int s_tile;
-    __shared__ unsigned long long s_lb[3 * NW + 2];
+    __shared__ unsigned long long s_prefix;
 
     const int tid = threadIdx.x;
     if (tid == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
@@ -95,9 +95,8 @@ __global__ void __launch_bounds__(FD_THREADS)
             }
         }
     }
-    const unsigned long long pre = lookback_block<FD_THREADS>(status, tile, tile_total, err, s_lb);
+    const unsigned long long pre = tile_exclusive_prefix(status, tile, tile_total, err, &s_prefix);
     if (tid == 0 && tile == num_tiles - 1) *total_out = pre + tile_total;
-    __syncthreads();
     for (unsigned i = tid; i < tile_total; i += FD_THREADS) {
         outK[pre + i] = s_ok[i];
         if (TAX) outT[pre + i] = s_ot[i];
@@ -230,6 +229,14 @@ extern "C" int ukm_fold_sorted(ukm_ctx* ctx, int mode, const ukm_span* in, unsig
     return ukm_deliver(ctx, ok, tax ? ot : nullptr, m, out);
 }
 
+int ukm_dev_check_sorted_unique(ukm_ctx* ctx, const uint64_t* d_keys, size_t n) {
+    if (n < 2) return UKM_OK;
+    ukm_stat_scope st(ctx, "validate_sorted_unique", 8.0 * (double)n);
+    check_sorted_unique_kernel<<<ukm_grid_for(n, 256 * 8, ctx->sm_count), 256, 0, ctx->stream>>>(d_keys, n, ctx->d_err);
+    UKM_LAUNCHED(ctx);
+    return UKM_OK;
+}
+
 extern "C" int ukm_check_sorted_unique(ukm_ctx* ctx, const ukm_span* in) {
     if (!ctx) return UKM_E_ARG;
     if (!in) return ukm_fail(ctx, UKM_E_ARG, "ukm_check_sorted_unique: NULL span");
@@ -238,8 +245,7 @@ extern "C" int ukm_check_sorted_unique(ukm_ctx* ctx, const ukm_span* in) {
     ukm_tmp tmp(ctx);
     ukm_dspan d;
     UKM_TRY(ukm_stage_in(ctx, tmp, in, false, &d));
-    check_sorted_unique_kernel<<<ukm_grid_for(d.n, 256 * 8, ctx->sm_count), 256, 0, ctx->stream>>>(d.keys, d.n, ctx->d_err);
-    UKM_LAUNCHED(ctx);
+    UKM_TRY(ukm_dev_check_sorted_unique(ctx, d.keys, d.n));
     return ukm_check_dev_error(ctx, "ukm_check_sorted_unique");
 }
 

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(RADIX) radix_bases_kernel(const unsigned long 
 #define OS_FLAG_INCLUSIVE (2u << 30)
 #define OS_VALUE_MASK ((1u << 30) - 1)
 
-template <int THREADS, int ITEMS, bool PAIRS>
+template <int THREADS, int ITEMS, bool PAIRS, bool BALLOT_MATCH>
 __global__ void __launch_bounds__(THREADS)
     onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout, const uint32_t* __restrict__ vin,
                     uint32_t* __restrict__ vout, size_t n, int num_tiles, int shift, uint32_t mask,
@@ -153,24 +153,38 @@ __global__ void __launch_bounds__(THREADS)
         }
     }
 
-    // 2. rank inside the warp: peers with the same digit via match, one counter per (warp,digit)
+    // 2. rank inside the warp.  Phase A: peer masks of all items (independent: MATCH / ballots pipeline
+    //    freely).  Phase B: the only serial part, one shared-memory counter update per item: every
+    //    lane reads the (warp,digit) counter, the highest peer lane adds the peer count.
     uint32_t* wh = s_whist + warp * RADIX;
     uint32_t rank[ITEMS];
     const unsigned lt = lanemask_lt();
+    unsigned peers[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        int leader = 31 - __clz((int)peers);
-        uint32_t before = (uint32_t)__popc(peers & lt);
-        uint32_t old = 0;
-        if ((int)lane == leader) {
-            old = wh[d];
-            wh[d] = old + before + 1;
+        const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        if (BALLOT_MATCH) {
+            unsigned m = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < RADIX_BITS; ++b) {
+                const unsigned v = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+                m &= ((d >> b) & 1u) ? v : ~v;
+            }
+            peers[i] = m;
+        } else {
+            peers[i] = __match_any_sync(0xffffffffu, d);
         }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[i] = old + before;
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        const uint32_t before = (uint32_t)__popc(peers[i] & lt);
+        const uint32_t cnt = (uint32_t)__popc(peers[i]);
+        const uint32_t old = wh[d];
         __syncwarp();
+        if (before == cnt - 1) wh[d] = old + cnt;
+        __syncwarp();
+        rank[i] = old + before;
     }
     __syncthreads();
 
@@ -197,13 +211,13 @@ __global__ void __launch_bounds__(THREADS)
         uint32_t* my = status + (size_t)tile * RADIX + tid;
         uint32_t excl = 0;
         if (tile == 0) {
-            st_release_u32(my, OS_FLAG_INCLUSIVE | pub);
+            st_relaxed_u32(my, OS_FLAG_INCLUSIVE | pub);
         } else {
-            st_release_u32(my, OS_FLAG_PARTIAL | pub);
+            st_relaxed_u32(my, OS_FLAG_PARTIAL | pub);
             int j = tile - 1;
             unsigned spins = 0;
             while (true) {
-                uint32_t w = ld_acquire_u32(status + (size_t)j * RADIX + tid);
+                uint32_t w = ld_relaxed_u32(status + (size_t)j * RADIX + tid);
                 uint32_t flag = w >> 30;
                 if (flag == 0) {
                     if (++spins > UKM_WATCHDOG_SPINS) {
@@ -217,7 +231,7 @@ __global__ void __launch_bounds__(THREADS)
                 if (flag == 2 || j == 0) break;
                 --j;
             }
-            st_release_u32(my, OS_FLAG_INCLUSIVE | (excl + pub));
+            st_relaxed_u32(my, OS_FLAG_INCLUSIVE | (excl + pub));
         }
         unsigned long long gb = bases_in[tid];
         s_gbase[tid] = gb + excl - dstart;
@@ -259,20 +273,31 @@ size_t onesweep_smem() {
     return s + 16;
 }
 
-template <int THREADS, int ITEMS, bool PAIRS>
-int launch_onesweep(ukm_ctx* ctx, const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, size_t n, int shift,
+template <int THREADS, int ITEMS, bool PAIRS, bool BM>
+int launch_onesweep_v(ukm_ctx* ctx, const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, size_t n, int shift,
                     uint32_t mask, const unsigned long long* bases_in, unsigned long long* bases_out, uint32_t* status,
                     uint32_t* counter) {
     constexpr int TILE = THREADS * ITEMS;
     int num_tiles = (int)((n + TILE - 1) / TILE);
     size_t smem = onesweep_smem<THREADS, ITEMS, PAIRS>();
-    auto kern = onesweep_kernel<THREADS, ITEMS, PAIRS>;
+    auto kern = onesweep_kernel<THREADS, ITEMS, PAIRS, BM>;
     UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     UKM_CUDA(ctx, cudaMemsetAsync(status, 0, (size_t)num_tiles * RADIX * sizeof(uint32_t), ctx->stream));
     kern<<<num_tiles, THREADS, smem, ctx->stream>>>(kin, kout, vin, vout, n, num_tiles, shift, mask, bases_in, bases_out, status,
                                                     counter, ctx->d_err);
     UKM_LAUNCHED(ctx);
     return UKM_OK;
+}
+
+// UKM_SORT_MATCH=ballot selects the ballot-built peer masks instead of MATCH.ANY (A/B runs)
+template <int THREADS, int ITEMS, bool PAIRS>
+int launch_onesweep(ukm_ctx* ctx, const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, size_t n, int shift,
+                    uint32_t mask, const unsigned long long* bases_in, unsigned long long* bases_out, uint32_t* status,
+                    uint32_t* counter) {
+    const char* e = getenv("UKM_SORT_MATCH");
+    if (e && e[0] == 'b')
+        return launch_onesweep_v<THREADS, ITEMS, PAIRS, true>(ctx, kin, kout, vin, vout, n, shift, mask, bases_in, bases_out, status, counter);
+    return launch_onesweep_v<THREADS, ITEMS, PAIRS, false>(ctx, kin, kout, vin, vout, n, shift, mask, bases_in, bases_out, status, counter);
 }
 
 struct SortCfg {

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(SEL_THREADS)
     __shared__ uint64_t s_o[SEL_TILE];
     __shared__ unsigned s_scan[NW + 2];
     __shared__ int s_tile;
-    __shared__ unsigned long long s_lb[3 * NW + 2];
+    __shared__ unsigned long long s_prefix;
     const int tid = threadIdx.x;
     if (tid == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
     __syncthreads();
@@ -39,9 +39,8 @@ __global__ void __launch_bounds__(SEL_THREADS)
 #pragma unroll
     for (int j = 0; j < SEL_ITEMS; ++j)
         if (mask & (1u << j)) s_o[o++] = k[j];
-    const unsigned long long pre = lookback_block<SEL_THREADS>(status, tile, tile_total, err, s_lb);
+    const unsigned long long pre = tile_exclusive_prefix(status, tile, tile_total, err, &s_prefix);
     if (tid == 0 && tile == num_tiles - 1) *total_out = pre + tile_total;
-    __syncthreads();
     for (unsigned i = tid; i < tile_total; i += SEL_THREADS) out[pre + i] = s_o[i];
 }
 

@@ -13,6 +13,8 @@
 // are brought into shared memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier),
 // every thread walks VT merged elements with the reference's three-way compare, outputs
 // are compacted through shared memory and written as contiguous runs.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "lca.cuh"
 
@@ -52,11 +54,12 @@ __device__ __forceinline__ long long merge_path_global(const uint64_t* __restric
 // tile boundaries: part[2t] = A index, part[2t+1] = B index of the first element of tile t.
 // For the pairing ops an equal (A,B) pair is never split: the B twin joins the A side's tile.
 __global__ void setop_partition_kernel(const uint64_t* __restrict__ A, long long nA, const uint64_t* __restrict__ B, long long nB,
-                                       int num_tiles, int pairing, long long* __restrict__ part, int* __restrict__ err) {
+                                       int num_tiles, int tile_elems, int pairing, long long* __restrict__ part,
+                                       int* __restrict__ err) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > num_tiles) return;
     long long total = nA + nB;
-    long long diag = (long long)t * SO_TILE;
+    long long diag = (long long)t * tile_elems;
     if (diag > total) diag = total;
     long long a = merge_path_global(A, nA, B, nB, diag);
     long long b = diag - a;
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
     __shared__ int s_part[SO_THREADS + 1];  // packed (a << 16 | b) thread starts
     __shared__ unsigned s_scan[NW + 2];
     __shared__ int s_tile;
-    __shared__ unsigned long long s_lb[3 * NW + 2];
+    __shared__ unsigned long long s_prefix;
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
     }
     unsigned long long prefix;
     if (OP == OP_MERGE) prefix = (unsigned long long)(a_lo + b_lo);
-    else prefix = lookback_block<SO_THREADS>(p.status, tile, tile_total, p.err, s_lb);
+    else prefix = tile_exclusive_prefix(p.status, tile, tile_total, p.err, &s_prefix);
     if (tid == 0 && tile == p.num_tiles - 1) *p.total_out = prefix + tile_total;
     __syncthreads();
     const unsigned long long base = prefix;
@@ -308,6 +311,209 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
         p.outK[base + i] = s_k[i];
         if (TAX) p.outT[base + i] = s_t[i];
         if (CNT && p.outC) p.outC[base + i] = s_c[i];
+    }
+}
+
+
+// ---- keys-only fast path ----------------------------------------------------------------------
+// Same tiling, but the walk is stripped to the bone (no taxids/counts, no per-step validation:
+// UKM_F_VALIDATE checks inputs up front instead) and outputs are staged in a SEPARATE shared
+// buffer so staging needs no barrier against the input slices.  blockIdx.x is the tile id.
+template <int OP, int VT>
+__global__ void __launch_bounds__(SO_THREADS, (VT <= 15 ? 3 : 2)) setop_fast_kernel(const SetopArgs p) {
+    constexpr int T = SO_THREADS * VT;
+    constexpr int NW = SO_THREADS / 32;
+    extern __shared__ __align__(16) unsigned char so_smem[];
+    uint64_t* s_k = reinterpret_cast<uint64_t*>(so_smem);  // T + 8: both input slices
+    uint64_t* s_o = s_k + T + 8;                           // T + 8: staged outputs
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_part[SO_THREADS + 1];
+    __shared__ unsigned s_scan[NW + 2];
+    __shared__ unsigned long long s_prefix;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const long long a_lo = p.part[2 * tile], b_lo = p.part[2 * tile + 1];
+    const int na = (int)(p.part[2 * tile + 2] - a_lo), nb = (int)(p.part[2 * tile + 3] - b_lo);
+    const int hA = slice_offset(p.A, a_lo);
+    const int hB = slice_offset(p.B, b_lo);
+    const int offB = ((hA + na + 1) & ~1) + hB;
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&s_bar, slice_body_bytes(p.A, a_lo, na) + slice_body_bytes(p.B, b_lo, nb));
+        slice_issue(s_k, p.A, a_lo, na, &s_bar);
+        slice_issue(s_k + offB - hB, p.B, b_lo, nb, &s_bar);
+    }
+    __syncthreads();  // barrier object initialised + head/tail plain stores visible
+    if (!mbar_wait(&s_bar, 0)) {
+        if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+    }
+    const uint64_t* sA = s_k + hA;
+    const uint64_t* sB = s_k + offB;
+
+    const int total = na + nb;
+    {
+        int diag = tid * VT;
+        if (diag > total) diag = total;
+        int a = merge_path(sA, na, sB, nb, diag);
+        int b = diag - a;
+        if (OP != OP_MERGE) {
+            if (a > 0 && b < nb && sA[a - 1] == sB[b]) ++b;
+        }
+        s_part[tid] = (a << 16) | b;
+        if (tid == 0) s_part[SO_THREADS] = (na << 16) | nb;
+    }
+    __syncthreads();
+    int ai = s_part[tid] >> 16, bi = s_part[tid] & 0xffff;
+    const int a1 = s_part[tid + 1] >> 16, b1 = s_part[tid + 1] & 0xffff;
+
+    uint64_t outk[VT + 1];
+    unsigned emitmask = 0;
+    uint64_t ka = sA[ai], kb = sB[bi];  // reads past a slice end stay inside s_k and are never used
+#pragma unroll
+    for (int it = 0; it <= VT; ++it) {
+        const bool pa = ai < a1, pb = bi < b1;
+        const bool gt = ka > kb;
+        const bool takeA = pa && (!pb || !gt);
+        const bool takeB = pb && !takeA;
+        const bool eq = takeA && pb && (ka == kb);
+        bool emit;
+        if (OP == OP_INTER) emit = eq;
+        else if (OP == OP_DIFF) emit = takeA && !eq;
+        else emit = takeA || takeB;
+        outk[it] = (OP == OP_INTER || OP == OP_DIFF) ? ka : (takeA ? ka : kb);
+        emitmask |= (emit ? 1u : 0u) << it;
+        if (takeA) ka = sA[++ai];
+        if (takeB || (eq && OP != OP_MERGE)) kb = sB[++bi];
+    }
+
+    const unsigned cnt = (unsigned)__popc(emitmask);
+    unsigned tile_total;
+    const unsigned off = block_excl_scan_u32<SO_THREADS>(cnt, s_scan, &tile_total);
+    {
+        unsigned o = off;
+#pragma unroll
+        for (int it = 0; it <= VT; ++it) {
+            if (emitmask & (1u << it)) s_o[o++] = outk[it];
+        }
+    }
+    unsigned long long prefix;
+    if (OP == OP_MERGE) {
+        prefix = (unsigned long long)(a_lo + b_lo);
+        __syncthreads();
+    } else {
+        prefix = tile_exclusive_prefix(p.status, tile, tile_total, p.err, &s_prefix);
+    }
+    if (tid == 0 && tile == p.num_tiles - 1) *p.total_out = prefix + tile_total;
+    uint64_t* dst = p.outK + prefix;
+    for (unsigned i = tid; i < tile_total; i += SO_THREADS) dst[i] = s_o[i];
+}
+
+// ---- search path for skewed pairs (|B| >> |A|): inter / diff -------------------------------------
+// When the running set A is much smaller than the next file B (inter.go / diff.go after a few files),
+// walking all of B is wasted work: every thread looks its A elements up in B's window for the tile
+// (branch-free lower_bound over global memory, top levels L1/L2 resident) and A is compacted in order.
+constexpr int SS_THREADS = 256;
+constexpr int SS_ITEMS = 4;
+constexpr int SS_TILE = SS_THREADS * SS_ITEMS;
+
+// bpart[t] = lower_bound(B, A[t * SS_TILE]) for t < num_tiles, bpart[num_tiles] = nB
+__global__ void search_partition_kernel(const uint64_t* __restrict__ A, long long nA, const uint64_t* __restrict__ B, long long nB,
+                                        int num_tiles, long long* __restrict__ bpart) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > num_tiles) return;
+    if (t == num_tiles) {
+        bpart[t] = nB;
+        return;
+    }
+    const uint64_t x = A[(long long)t * SS_TILE];
+    long long lo = 0, hi = nB;
+    while (lo < hi) {
+        long long mid = lo + ((hi - lo) >> 1);
+        if (B[mid] < x) lo = mid + 1;
+        else hi = mid;
+    }
+    bpart[t] = lo;
+}
+
+template <int OP, bool TAX>
+__global__ void __launch_bounds__(SS_THREADS) setop_search_kernel(const SetopArgs p) {
+    constexpr int NW = SS_THREADS / 32;
+    __shared__ uint64_t s_o[SS_TILE];
+    __shared__ uint32_t s_ot[TAX ? SS_TILE : 1];
+    __shared__ unsigned s_scan[NW + 2];
+    __shared__ unsigned long long s_prefix;
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const long long base = (long long)tile * SS_TILE + (long long)tid * SS_ITEMS;
+    const long long blo = p.part[tile], bhi = p.part[tile + 1];
+    uint64_t a[SS_ITEMS];
+    long long pos[SS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SS_ITEMS; ++j) {
+        a[j] = (base + j < p.nA) ? p.A[base + j] : ~0ull;
+        pos[j] = blo;
+    }
+    // branch-free lower_bound (uniform trip count: n depends only on the window size), SS_ITEMS
+    // independent chains per thread.  Invariant: the answer lies in [pos, pos + n].
+    long long n = bhi - blo;
+    while (n > 1) {
+        const long long half = n >> 1;
+#pragma unroll
+        for (int j = 0; j < SS_ITEMS; ++j) {
+            const uint64_t v = __ldg(p.B + pos[j] + half);
+            if (v < a[j]) pos[j] += half;
+        }
+        n -= half;
+    }
+    if (n == 1) {
+#pragma unroll
+        for (int j = 0; j < SS_ITEMS; ++j)
+            if (__ldg(p.B + pos[j]) < a[j]) pos[j] += 1;
+    }
+    unsigned mask = 0;
+    uint32_t tx[TAX ? SS_ITEMS : 1] = {0};
+#pragma unroll
+    for (int j = 0; j < SS_ITEMS; ++j) {
+        bool valid = base + j < p.nA;
+        bool found = valid && pos[j] < bhi && p.B[pos[j]] == a[j];
+        bool emit = valid && (OP == OP_INTER ? found : !found);
+        if (TAX && valid) {
+            uint32_t qa = p.tA[base + j];
+            if (OP == OP_INTER) {
+                if (found) {
+                    uint32_t qb = p.tB[pos[j]];
+                    if (p.flags & UKM_F_MIX_TAXID) tx[j] = qa == 0 ? qb : (qb == 0 ? qa : lca_dev(p.tax, qa, qb));
+                    else tx[j] = lca_dev(p.tax, qa, qb);
+                }
+            } else {
+                tx[j] = qa;
+                if (found && (p.flags & UKM_F_COMPARE_TAXID)) {
+                    uint32_t qb = p.tB[pos[j]];
+                    if (qa == qb || lca_dev(p.tax, qb, qa) == qa) emit = true;
+                }
+            }
+        }
+        if (emit) mask |= 1u << j;
+    }
+    unsigned tile_total;
+    const unsigned off = block_excl_scan_u32<SS_THREADS>((unsigned)__popc(mask), s_scan, &tile_total);
+    {
+        unsigned o = off;
+#pragma unroll
+        for (int j = 0; j < SS_ITEMS; ++j)
+            if (mask & (1u << j)) {
+                s_o[o] = a[j];
+                if (TAX) s_ot[o] = tx[j];
+                ++o;
+            }
+    }
+    const unsigned long long prefix = tile_exclusive_prefix(p.status, tile, tile_total, p.err, &s_prefix);
+    if (tid == 0 && tile == p.num_tiles - 1) *p.total_out = prefix + tile_total;
+    for (unsigned i = tid; i < tile_total; i += SS_THREADS) {
+        p.outK[prefix + i] = s_o[i];
+        if (TAX) p.outT[prefix + i] = s_ot[i];
     }
 }
 
@@ -354,6 +560,43 @@ const char* op_name(int op, bool tax) {
     }
 }
 
+template <int OP, int VT>
+int launch_fast_v(ukm_ctx* ctx, const SetopArgs& a) {
+    constexpr size_t smem = (size_t)2 * (SO_THREADS * VT + 8) * 8;
+    auto kern = setop_fast_kernel<OP, VT>;
+    static bool configured = false;
+    if (!configured) {
+        UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<a.num_tiles, SO_THREADS, smem, ctx->stream>>>(a);
+    UKM_LAUNCHED(ctx);
+    return UKM_OK;
+}
+
+template <int VT>
+int launch_fast(ukm_ctx* ctx, int op, const SetopArgs& a) {
+    switch (op) {
+        case OP_INTER: return launch_fast_v<OP_INTER, VT>(ctx, a);
+        case OP_DIFF: return launch_fast_v<OP_DIFF, VT>(ctx, a);
+        case OP_UNION: return launch_fast_v<OP_UNION, VT>(ctx, a);
+        default: return launch_fast_v<OP_MERGE, VT>(ctx, a);
+    }
+}
+
+// merged elements per thread of the keys-only kernel; UKM_SETOP_VT overrides for A/B runs
+int fast_vt() {
+    const char* e = getenv("UKM_SETOP_VT");
+    int v = e ? atoi(e) : 15;
+    return (v == 11 || v == 15 || v == 19 || v == 23) ? v : 15;
+}
+
+// |B| >= SKEW * |A| => look A up in B instead of walking B (UKM_SETOP_SKEW overrides; 0 disables)
+long long search_skew() {
+    const char* e = getenv("UKM_SETOP_SKEW");
+    return e ? atoll(e) : 3;
+}
+
 // out buffers must hold: INTER min(nA,nB); DIFF nA; UNION/MERGE nA+nB.  *n_out gets the count
 // (host value, after a stream sync).
 int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, bool cnt, unsigned flags, uint32_t threshold,
@@ -364,48 +607,70 @@ int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, boo
         out->n = 0;
         return UKM_OK;
     }
-    const int num_tiles = (int)((total + SO_TILE - 1) / SO_TILE);
+    const long long skew = search_skew();
+    const bool use_search = (op == OP_INTER || op == OP_DIFF) && !cnt && nA > 0 && skew > 0 && nB >= skew * nA;
+    const bool use_fast = !use_search && !tax && !cnt;
+    const int vt = fast_vt();
+    const int tile_elems = use_search ? SS_TILE : (use_fast ? SO_THREADS * vt : SO_TILE);
+    const int num_tiles = (int)(((use_search ? nA : total) + tile_elems - 1) / tile_elems);
     ukm_tmp tmp(ctx);
     long long* d_part = nullptr;
     uint64_t* d_status = nullptr;
-    uint32_t* d_counter = nullptr;
-    unsigned long long* d_total = nullptr;
     UKM_TRY(tmp.alloc(&d_part, (size_t)2 * (num_tiles + 1)));
     UKM_TRY(tmp.alloc(&d_status, (size_t)num_tiles + 4));
-    // d_counter and d_total live in the tail of the status allocation (zeroed together)
-    d_counter = reinterpret_cast<uint32_t*>(d_status + num_tiles);
-    d_total = reinterpret_cast<unsigned long long*>(d_status + num_tiles + 1);
+    // tile counter and output total live in the tail of the status allocation (zeroed together)
+    uint32_t* d_counter = reinterpret_cast<uint32_t*>(d_status + num_tiles);
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(d_status + num_tiles + 1);
     UKM_CUDA(ctx, cudaMemsetAsync(d_status, 0, ((size_t)num_tiles + 4) * sizeof(uint64_t), ctx->stream));
 
+    SetopArgs a;
+    a.A = A.k; a.tA = A.t; a.cA = A.c; a.nA = nA;
+    a.B = B.k; a.tB = B.t; a.cB = B.c; a.nB = nB;
+    a.part = d_part;
+    a.outK = out->k; a.outT = out->t; a.outC = out->c;
+    a.status = d_status; a.tile_counter = d_counter; a.total_out = d_total;
+    a.num_tiles = num_tiles;
+    a.flags = flags;
+    a.threshold = threshold;
+    a.tax = ukm_taxdev(ctx);
+    a.err = ctx->d_err;
     {
+        // algorithmic bytes: both inputs read once (+ the output, added below)
         ukm_stat_scope st(ctx, op_name(op, tax), (double)total * (tax ? 12.0 : 8.0));
-        setop_partition_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(A.k, nA, B.k, nB, num_tiles, op != OP_MERGE,
-                                                                                     d_part, ctx->d_err);
-        UKM_LAUNCHED(ctx);
-        SetopArgs a;
-        a.A = A.k; a.tA = A.t; a.cA = A.c; a.nA = nA;
-        a.B = B.k; a.tB = B.t; a.cB = B.c; a.nB = nB;
-        a.part = d_part;
-        a.outK = out->k; a.outT = out->t; a.outC = out->c;
-        a.status = d_status; a.tile_counter = d_counter; a.total_out = d_total;
-        a.num_tiles = num_tiles;
-        a.flags = flags;
-        a.threshold = threshold;
-        a.tax = ukm_taxdev(ctx);
-        a.err = ctx->d_err;
         int r;
-        switch (op) {
-            case OP_INTER: r = launch_setop<OP_INTER>(ctx, tax, false, a); break;
-            case OP_DIFF: r = launch_setop<OP_DIFF>(ctx, tax, false, a); break;
-            case OP_UNION: r = launch_setop<OP_UNION>(ctx, tax, cnt, a); break;
-            default: r = launch_setop<OP_MERGE>(ctx, tax, false, a); break;
+        if (use_search) {
+            search_partition_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(A.k, nA, B.k, nB, num_tiles, d_part);
+            UKM_LAUNCHED(ctx);
+            if (op == OP_INTER) {
+                if (tax) setop_search_kernel<OP_INTER, true><<<num_tiles, SS_THREADS, 0, ctx->stream>>>(a);
+                else setop_search_kernel<OP_INTER, false><<<num_tiles, SS_THREADS, 0, ctx->stream>>>(a);
+            } else {
+                if (tax) setop_search_kernel<OP_DIFF, true><<<num_tiles, SS_THREADS, 0, ctx->stream>>>(a);
+                else setop_search_kernel<OP_DIFF, false><<<num_tiles, SS_THREADS, 0, ctx->stream>>>(a);
+            }
+            UKM_LAUNCHED(ctx);
+            r = UKM_OK;
+        } else {
+            setop_partition_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(A.k, nA, B.k, nB, num_tiles, tile_elems,
+                                                                                         op != OP_MERGE, d_part, ctx->d_err);
+            UKM_LAUNCHED(ctx);
+            if (use_fast) {
+                r = vt == 11 ? launch_fast<11>(ctx, op, a) : vt == 19 ? launch_fast<19>(ctx, op, a)
+                  : vt == 23 ? launch_fast<23>(ctx, op, a) : launch_fast<15>(ctx, op, a);
+            } else {
+                switch (op) {
+                    case OP_INTER: r = launch_setop<OP_INTER>(ctx, tax, false, a); break;
+                    case OP_DIFF: r = launch_setop<OP_DIFF>(ctx, tax, false, a); break;
+                    case OP_UNION: r = launch_setop<OP_UNION>(ctx, tax, cnt, a); break;
+                    default: r = launch_setop<OP_MERGE>(ctx, tax, false, a); break;
+                }
+            }
         }
         UKM_TRY(r);
     }
     UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     out->n = (size_t)ctx->h_scratch[0];
-    // algorithmic bytes = inputs read once + output written once
     if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes += (double)out->n * (tax ? 12.0 : 8.0);
     return UKM_OK;
 }
@@ -424,7 +689,7 @@ void free_set(ukm_tmp& tmp, DevSet* s) {
     *s = DevSet();
 }
 
-int stage_set(ukm_ctx* ctx, ukm_tmp& tmp, const ukm_span* in, bool tax, DevSet* s, bool* owned) {
+int stage_set(ukm_ctx* ctx, ukm_tmp& tmp, const ukm_span* in, bool tax, DevSet* s, bool* owned, bool validate = false) {
     ukm_dspan d;
     size_t before = tmp.ptrs.size();
     UKM_TRY(ukm_stage_in(ctx, tmp, in, tax, &d));
@@ -433,6 +698,7 @@ int stage_set(ukm_ctx* ctx, ukm_tmp& tmp, const ukm_span* in, bool tax, DevSet* 
     s->t = d.taxids;
     s->c = nullptr;
     s->n = d.n;
+    if (validate && d.n > 1) UKM_TRY(ukm_dev_check_sorted_unique(ctx, d.keys, d.n));
     return UKM_OK;
 }
 // free whatever stage_set allocated for this span (device spans are left alone)
@@ -467,7 +733,8 @@ int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags
     ukm_tmp tmp(ctx);
     DevSet cur, nxt, F;
     bool owned;
-    UKM_TRY(stage_set(ctx, tmp, &in[0], tax, &cur, &owned));
+    const bool validate = (flags & UKM_F_VALIDATE) != 0;
+    UKM_TRY(stage_set(ctx, tmp, &in[0], tax, &cur, &owned, validate));
     bool cur_is_input = true;  // cur aliases the staged in[0]
     const size_t cap = in[0].n;
     DevSet bufs[2];
@@ -479,7 +746,7 @@ int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags
         }
         if (op == OP_DIFF && in[i].n == 0) continue;
         if (cur.n == 0) break;
-        UKM_TRY(stage_set(ctx, tmp, &in[i], tax, &F, &owned));
+        UKM_TRY(stage_set(ctx, tmp, &in[i], tax, &F, &owned, validate && !(op == OP_DIFF && !in[i].sorted)));
         if (op == OP_DIFF && !in[i].sorted) {
             // diff.go:341-367 handles an unsorted subject through a map; here: sort a private copy,
             // then drop duplicate codes (a map delete is idempotent)
@@ -529,7 +796,7 @@ int run_tree(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags,
     std::vector<int> src(n_in);  // index into `in` while the set is still a staged input, else -1
     for (int i = 0; i < n_in; ++i) {
         bool owned;
-        UKM_TRY(stage_set(ctx, tmp, &in[i], tax, &level[i], &owned));
+        UKM_TRY(stage_set(ctx, tmp, &in[i], tax, &level[i], &owned, (flags & UKM_F_VALIDATE) != 0 && op != OP_MERGE));
         src[i] = i;
     }
     // a single input still goes through one pass against an empty set so thresholds apply
@@ -598,13 +865,13 @@ extern "C" int ukm_diff(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned fla
 extern "C" int ukm_union(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_span* out) {
     UKM_TRY(check_args(ctx, in, n_in, out, "ukm_union"));
     UKM_TRY(need_tax(ctx, flags & UKM_F_TAXID, "ukm_union"));
-    return run_tree(ctx, OP_UNION, in, n_in, flags & UKM_F_TAXID, false, 0, UKM_FOLD_PLAIN, out, "ukm_union");
+    return run_tree(ctx, OP_UNION, in, n_in, flags & (UKM_F_TAXID | UKM_F_VALIDATE), false, 0, UKM_FOLD_PLAIN, out, "ukm_union");
 }
 
 extern "C" int ukm_common(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, uint16_t threshold, ukm_span* out) {
     UKM_TRY(check_args(ctx, in, n_in, out, "ukm_common"));
     UKM_TRY(need_tax(ctx, flags & UKM_F_TAXID, "ukm_common"));
-    return run_tree(ctx, OP_UNION, in, n_in, flags & UKM_F_TAXID, true, threshold, UKM_FOLD_PLAIN, out, "ukm_common");
+    return run_tree(ctx, OP_UNION, in, n_in, flags & (UKM_F_TAXID | UKM_F_VALIDATE), true, threshold, UKM_FOLD_PLAIN, out, "ukm_common");
 }
 
 extern "C" int ukm_merge_sorted(ukm_ctx* ctx, int mode, const ukm_span* in, int n_in, unsigned flags, ukm_span* out) {

@@ -234,34 +234,34 @@ class Engine:
         return self._trim(out, k, t)
 
     # ---- set operations ---------------------------------------------------------------------
-    def union(self, sets: Sequence, has_taxid: bool = False, out=None):
+    def union(self, sets: Sequence, has_taxid: bool = False, out=None, validate: bool = False):
         """`unikmer union -s` (union.go:186-208, 260-305)."""
         arr, keep, dev = self._spans(sets)
         out, k, t = self._span_out(sum(int(a.n) for a in arr), has_taxid, dev, out)
-        self._chk(self.lib.ukm_union(self.ctx, arr, len(arr), L.F_TAXID if has_taxid else 0, C.byref(out)))
+        self._chk(self.lib.ukm_union(self.ctx, arr, len(arr), (L.F_TAXID if has_taxid else 0) | (L.F_VALIDATE if validate else 0), C.byref(out)))
         return self._trim(out, k, t)
 
-    def inter(self, sets: Sequence, has_taxid: bool = False, mix_taxid: bool = False, out=None):
+    def inter(self, sets: Sequence, has_taxid: bool = False, mix_taxid: bool = False, out=None, validate: bool = False):
         """`unikmer inter [--mix-taxid]` (inter.go:188-286), iterated in file order."""
         arr, keep, dev = self._spans(sets)
-        flags = (L.F_TAXID if has_taxid else 0) | (L.F_MIX_TAXID if mix_taxid else 0)
+        flags = (L.F_TAXID if has_taxid else 0) | (L.F_MIX_TAXID if mix_taxid else 0) | (L.F_VALIDATE if validate else 0)
         out, k, t = self._span_out(int(arr[0].n), has_taxid or mix_taxid, dev, out)
         self._chk(self.lib.ukm_inter(self.ctx, arr, len(arr), flags, C.byref(out)))
         return self._trim(out, k, t)
 
-    def diff(self, sets: Sequence, has_taxid: bool = False, compare_taxid: bool = False, out=None):
+    def diff(self, sets: Sequence, has_taxid: bool = False, compare_taxid: bool = False, out=None, validate: bool = False):
         """`unikmer diff -s [-t]` (diff.go:136-146, 341-515, 566-594)."""
         arr, keep, dev = self._spans(sets)
-        flags = (L.F_TAXID if has_taxid else 0) | (L.F_COMPARE_TAXID if compare_taxid else 0)
+        flags = (L.F_TAXID if has_taxid else 0) | (L.F_COMPARE_TAXID if compare_taxid else 0) | (L.F_VALIDATE if validate else 0)
         out, k, t = self._span_out(int(arr[0].n), has_taxid, dev, out)
         self._chk(self.lib.ukm_diff(self.ctx, arr, len(arr), flags, C.byref(out)))
         return self._trim(out, k, t)
 
-    def common(self, sets: Sequence, threshold: int, has_taxid: bool = False):
+    def common(self, sets: Sequence, threshold: int, has_taxid: bool = False, validate: bool = False):
         """`unikmer common -n threshold` (common.go:220-283, 329-354)."""
         arr, keep, dev = self._spans(sets)
         out, k, t = self._span_out(sum(int(a.n) for a in arr), has_taxid, dev)
-        self._chk(self.lib.ukm_common(self.ctx, arr, len(arr), L.F_TAXID if has_taxid else 0, threshold, C.byref(out)))
+        self._chk(self.lib.ukm_common(self.ctx, arr, len(arr), (L.F_TAXID if has_taxid else 0) | (L.F_VALIDATE if validate else 0), threshold, C.byref(out)))
         return self._trim(out, k, t)
 
     def merge(self, sets: Sequence, mode: int = L.FOLD_PLAIN, has_taxid: bool = False):
