@@ -193,18 +193,27 @@ def member_files(N, nfiles, S=3, T=4):
     return [oracle.member_file(0, N, N, S, T, f) for f in range(nfiles)]
 
 
-@pytest.mark.parametrize("vt", ["11", "15", "19", "23"])
+@pytest.mark.parametrize("kernel", ["pipe:15,3", "pipe:11,4", "pipe:11,3", "pipe:15,4", "vt:11", "vt:15", "vt:19", "vt:23"])
 @pytest.mark.parametrize("skew", ["0", "3"])
-def test_setop_kernel_variants(eng, vt, skew, monkeypatch):
-    """Every tile shape of the keys-only merge kernel, with and without the search path for skewed pairs."""
-    monkeypatch.setenv("UKM_SETOP_VT", vt)
+def test_setop_kernel_variants(eng, kernel, skew, monkeypatch):
+    """Every shape of the keys-only kernels (persistent pipeline / one tile per CTA), with and without
+    the search path for skewed pairs."""
+    kind, cfg = kernel.split(":")
+    monkeypatch.setenv("UKM_SETOP_PIPE", cfg if kind == "pipe" else "0")
+    if kind == "vt":
+        monkeypatch.setenv("UKM_SETOP_VT", cfg)
     monkeypatch.setenv("UKM_SETOP_SKEW", skew)
-    files = member_files(400_000, 8)
-    same(eng.inter(files)[0], oracle.inter(files)[0], "inter")
-    same(eng.diff(files)[0], oracle.diff(files)[0], "diff")
-    same(eng.union(files)[0], oracle.union(files)[0], "union")
-    chunks = [np.sort(rng(3).integers(0, 90_000, n).astype(U64)) for n in (120_000, 7, 55_555)]
+    for N, nf in ((400_000, 8), (3_000_000, 3), (5_000, 2)):
+        files = member_files(N, nf)
+        same(eng.inter(files)[0], oracle.inter(files)[0], f"inter {N}")
+        same(eng.diff(files)[0], oracle.diff(files)[0], f"diff {N}")
+        same(eng.union(files)[0], oracle.union(files)[0], f"union {N}")
+    chunks = [np.sort(rng(3).integers(0, 90_000, n).astype(U64)) for n in (120_000, 7, 55_555, 2_000_000)]
     same(eng.merge(chunks, oracle.FOLD_PLAIN)[0], oracle.merge_chunks(chunks, oracle.FOLD_PLAIN)[0], "merge")
+    import torch
+    d = [torch.from_numpy(f.view(np.int64)).cuda()[1:] for f in member_files(1_000_000, 2)]  # 8 mod 16 pointers
+    exp = oracle.union([x.cpu().numpy().view(U64) for x in d])[0]
+    same(eng.union(d)[0].cpu().numpy().view(U64), exp, "unaligned union")
 
 
 def test_search_path_skewed_pairs(eng, tax):

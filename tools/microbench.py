@@ -63,8 +63,9 @@ def main():
             U = n
             files = [eng.synth_member_file(0, U, U, 3, 4, f).clone() for f in range(8)]
             tot = sum(int(f.shape[0]) for f in files)
-            for vt, skew in [("15", "0"), ("11", "3"), ("15", "3"), ("19", "3"), ("23", "3")]:
-                os.environ["UKM_SETOP_VT"], os.environ["UKM_SETOP_SKEW"] = vt, skew
+            for pipe, vt, skew in [("0", "15", "3"), ("0", "23", "3"), ("15,3", "15", "3"), ("11,4", "15", "3"), ("11,3", "15", "3"),
+                                   ("15,4", "15", "3"), ("15,3", "15", "0")]:
+                os.environ["UKM_SETOP_PIPE"], os.environ["UKM_SETOP_VT"], os.environ["UKM_SETOP_SKEW"] = pipe, vt, skew
                 res = {}
                 for name in ("inter", "diff", "union"):
                     fn = getattr(eng, name)
@@ -74,8 +75,8 @@ def main():
                     st = eng.stats()
                     res[name] = {"ms": round(ms, 3), "kmers_per_s": tot / ms * 1e3,
                                  "launch_ms": [round(v["ms"] / 4, 3) for k, v in st.items() if k.startswith("setop")]}
-                print(json.dumps({"bench": "setops_C3", "universe": U, "vt": vt, "skew": skew, **res}), flush=True)
-            os.environ.pop("UKM_SETOP_VT", None); os.environ.pop("UKM_SETOP_SKEW", None)
+                print(json.dumps({"bench": "setops_C3", "universe": U, "pipe": pipe, "vt": vt, "skew": skew, **res}), flush=True)
+            os.environ.pop("UKM_SETOP_VT", None); os.environ.pop("UKM_SETOP_SKEW", None); os.environ.pop("UKM_SETOP_PIPE", None)
             del files
         if "pairs" in what:
             m = n // 2

@@ -235,6 +235,13 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barrier over `nthreads` threads (warp-specialised kernels: consumers only)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
     unsigned ok;
     asm volatile(
@@ -356,12 +363,95 @@ __device__ __forceinline__ uint64_t lookback_warp(uint64_t* status, int tile, ui
     return prefix;
 }
 
+// 256-wide variant: every lane inspects 8 consecutive predecessors (nearest first), so one round
+// covers every tile that can be resident at once (a 32-wide window needs ~N_resident/64 serial L2
+// round trips when a wave of tiles publishes together: measured 20% of the kernel).  `publish`
+// = also write this tile's PARTIAL word first.  Called by all lanes of one warp.
+__device__ __forceinline__ uint64_t lookback_wide(uint64_t* status, int tile, uint64_t aggregate, bool publish, int* err) {
+    const unsigned l = lane_id();
+    if (tile == 0) {
+        if (l == 0) st_relaxed_u64(&status[0], UKM_LB_INCLUSIVE | aggregate);
+        return 0;
+    }
+    if (publish && l == 0) st_relaxed_u64(&status[tile], UKM_LB_PARTIAL | aggregate);
+    uint64_t prefix = 0;
+    int base = tile - 1;  // lane l inspects tiles base - 8l - m, m = 0..7
+    unsigned spins = 0;
+    while (true) {
+        uint64_t w[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int j = base - 8 * (int)l - m;
+            w[m] = (j >= 0) ? ld_relaxed_u64(&status[j]) : UKM_LB_INCLUSIVE;
+        }
+        uint64_t sum = 0;
+        unsigned state = 0, taken = 8;  // state: 0 all partial, 1 stopped at an empty word, 2 hit an inclusive word
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const unsigned flag = (unsigned)(w[m] >> 62);
+            if (state == 0) {
+                if (flag == 0) {
+                    state = 1;
+                    taken = m;
+                } else {
+                    sum += UKM_LB_VALUE(w[m]);
+                    if (flag == 2) {
+                        state = 2;
+                        taken = m + 1;
+                    }
+                }
+            }
+        }
+        const unsigned stopped = __ballot_sync(0xffffffffu, state != 0);
+        const unsigned f = stopped ? (unsigned)(__ffs(stopped) - 1) : 32u;  // first lane that stopped
+        uint64_t v = (l <= f) ? sum : 0ull;                                  // lanes before it contribute fully
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        prefix += v;
+        const unsigned fstate = __shfl_sync(0xffffffffu, state, f & 31u);
+        const unsigned ftaken = __shfl_sync(0xffffffffu, taken, f & 31u);
+        if (f < 32u && fstate == 2) break;
+        const unsigned consumed = (f < 32u) ? 8u * f + ftaken : 256u;
+        base -= (int)consumed;
+        if (consumed == 0) {
+            if (++spins > UKM_WATCHDOG_SPINS) {
+                if (l == 0) atomicExch(err, (int)UKM_E_INTERNAL);
+                prefix = 0;
+                break;
+            }
+        } else {
+            spins = 0;
+        }
+    }
+    if (l == 0) st_relaxed_u64(&status[tile], UKM_LB_INCLUSIVE | (prefix + aggregate));
+    return prefix;
+}
+
+// block_excl_scan_u32 over the NTHREADS threads of a named barrier (tid = index within that group)
+template <int NTHREADS>
+__device__ __forceinline__ unsigned group_excl_scan_u32(unsigned v, unsigned tid, unsigned* ws, unsigned* total, int bar_id) {
+    constexpr int NW = NTHREADS / 32;
+    unsigned incl = warp_incl_scan_u32(v);
+    unsigned w = tid >> 5, l = lane_id();
+    if (l == 31) ws[w] = incl;
+    named_bar_sync(bar_id, NTHREADS);
+    if (w == 0) {
+        unsigned x = (l < NW) ? ws[l] : 0u;
+        unsigned xi = warp_incl_scan_u32(x);
+        if (l < NW) ws[l] = xi - x;
+        if (l == NW - 1) ws[NW] = xi;
+    }
+    named_bar_sync(bar_id, NTHREADS);
+    *total = ws[NW];
+    return ws[w] + incl - v;
+}
+
 // All threads call this after staging their outputs: warp 0 chains the tile total, the barrier
 // publishes both the prefix and the staged data.  `s_prefix` is one shared 64-bit word.
 __device__ __forceinline__ uint64_t tile_exclusive_prefix(uint64_t* status, int tile, uint64_t tile_total, int* err,
                                                           unsigned long long* s_prefix) {
     if (threadIdx.x < 32) {
-        uint64_t pre = lookback_warp(status, tile, tile_total, err);
+        uint64_t pre = lookback_wide(status, tile, tile_total, true, err);
         if (threadIdx.x == 0) *s_prefix = pre;
     }
     __syncthreads();

@@ -102,6 +102,27 @@ __device__ __forceinline__ void slice_issue(T* s, const T* g, long long start, i
     for (int i = head + body; i < count; ++i) s[h + i] = g[start + i];
 }
 
+// the same, split so a producer can do the plain part before arming the barrier
+template <typename T>
+__device__ __forceinline__ void slice_issue_plain(T* s, const T* g, long long start, int count) {
+    constexpr int PER16 = 16 / sizeof(T);
+    int h = slice_offset(g, start);
+    int head = h ? (PER16 - h) : 0;
+    if (head > count) head = count;
+    int body = ((count - head) / PER16) * PER16;
+    for (int i = 0; i < head; ++i) s[h + i] = g[start + i];
+    for (int i = head + body; i < count; ++i) s[h + i] = g[start + i];
+}
+template <typename T>
+__device__ __forceinline__ void slice_issue_bulk(T* s, const T* g, long long start, int count, uint64_t* bar) {
+    constexpr int PER16 = 16 / sizeof(T);
+    int h = slice_offset(g, start);
+    int head = h ? (PER16 - h) : 0;
+    if (head > count) head = count;
+    int body = ((count - head) / PER16) * PER16;
+    if (body) tma_load_1d(s + h + head, g + start + head, (unsigned)(body * sizeof(T)), bar);
+}
+
 struct SetopArgs {
     const uint64_t* A;
     const uint32_t* tA;
@@ -410,6 +431,204 @@ __global__ void __launch_bounds__(SO_THREADS, (VT <= 15 ? 3 : 2)) setop_fast_ker
     for (unsigned i = tid; i < tile_total; i += SO_THREADS) dst[i] = s_o[i];
 }
 
+
+// ---- persistent, warp-specialised pipeline (keys-only) ----------------------------------------------
+// One producer warp + SO_THREADS consumer threads per CTA, CTAs resident for the whole launch, tiles
+// taken round-robin (tile = blockIdx.x + i * gridDim.x).  A ring of SLOTS shared-memory tile slots:
+//   producer : waits for a free slot, reads the tile geometry, issues the two TMA bulk loads
+//              (full[s] mbarrier), and -- off the consumers' critical path -- chains the tile's output
+//              count to its predecessors (decoupled look-back) and posts the prefix (pre[s]).
+//   consumers: wait full[s]; merge-path search; three-way walk; scan; stage the outputs IN PLACE in the
+//              slot; post the count (cnt[s]); then copy the PREVIOUS tile out (its prefix has had a whole
+//              tile's worth of time to arrive) and hand its slot back (empty[s]).
+// Global-memory latency (geometry, TMA, look-back) never stalls the merging warps.
+struct PipeGeom {
+    long long base;  // a_lo + b_lo (merged rank of the tile start)
+    int na, nb, hA, offB;
+};
+
+template <int OP, int VT, int SLOTS>
+__global__ void __launch_bounds__(SO_THREADS + 32, 2) setop_pipe_kernel(const SetopArgs p) {
+    constexpr int NT = SO_THREADS;  // consumer threads
+    constexpr int T = NT * VT;
+    constexpr int SLOT = T + 8;
+    constexpr int NW = NT / 32;
+    extern __shared__ __align__(16) unsigned char so_smem[];
+    uint64_t* s_slots = reinterpret_cast<uint64_t*>(so_smem);  // SLOTS * SLOT
+    __shared__ __align__(8) uint64_t full_bar[SLOTS], empty_bar[SLOTS], cnt_bar[SLOTS], pre_bar[SLOTS];
+    __shared__ unsigned long long s_cnt[SLOTS], s_pre[SLOTS];
+    __shared__ PipeGeom s_geom[SLOTS];
+    __shared__ int s_part[NT + 1];
+    __shared__ unsigned s_scan[NW + 2];
+
+    const int G = gridDim.x;
+    const int n_my = (p.num_tiles - (int)blockIdx.x + G - 1) / G;  // tiles of this CTA
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SLOTS; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NT);  // every consumer thread arrives after its share of the copy-out
+            mbar_init(&cnt_bar[s], 1);
+            mbar_init(&pre_bar[s], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (threadIdx.x < 32) {
+        // ================= producer / look-back warp =================
+        const unsigned lane = threadIdx.x;
+        int li = 0, bi = 0;  // next tile (local index) to load / to chain
+        unsigned idle = 0;
+        while (li < n_my || (OP != OP_MERGE && bi < n_my)) {
+            bool progressed = false;
+            if (li < n_my) {
+                const int s = li % SLOTS, u = li / SLOTS;
+                const bool slot_free = (u == 0) || mbar_try_wait(&empty_bar[s], (unsigned)(u - 1) & 1u);
+                if (slot_free) {
+                    if (lane == 0) {
+                        const int tile = (int)blockIdx.x + li * G;
+                        const long long a_lo = p.part[2 * tile], b_lo = p.part[2 * tile + 1];
+                        const int na = (int)(p.part[2 * tile + 2] - a_lo), nb = (int)(p.part[2 * tile + 3] - b_lo);
+                        const int hA = slice_offset(p.A, a_lo), hB = slice_offset(p.B, b_lo);
+                        const int offB = ((hA + na + 1) & ~1) + hB;
+                        uint64_t* slot = s_slots + (size_t)s * SLOT;
+                        PipeGeom g;
+                        g.base = a_lo + b_lo;
+                        g.na = na; g.nb = nb; g.hA = hA; g.offB = offB;
+                        s_geom[s] = g;
+                        // head/tail elements by plain stores, bodies by TMA; the arrive (release) publishes both
+                        const unsigned bytes = slice_body_bytes(p.A, a_lo, na) + slice_body_bytes(p.B, b_lo, nb);
+                        slice_issue_plain(slot, p.A, a_lo, na);
+                        slice_issue_plain(slot + offB - hB, p.B, b_lo, nb);
+                        mbar_expect_tx(&full_bar[s], bytes);
+                        slice_issue_bulk(slot, p.A, a_lo, na, &full_bar[s]);
+                        slice_issue_bulk(slot + offB - hB, p.B, b_lo, nb, &full_bar[s]);
+                    }
+                    __syncwarp();
+                    ++li;
+                    progressed = true;
+                }
+            }
+            if (OP != OP_MERGE && bi < li) {
+                const int s = bi % SLOTS, u = bi / SLOTS;
+                if (mbar_try_wait(&cnt_bar[s], (unsigned)u & 1u)) {
+                    const int tile = (int)blockIdx.x + bi * G;
+                    const unsigned long long total = s_cnt[s];
+                    const unsigned long long prefix = lookback_wide(p.status, tile, total, false, p.err);
+                    if (lane == 0) {
+                        s_pre[s] = prefix;
+                        if (tile == p.num_tiles - 1) *p.total_out = prefix + total;
+                        mbar_arrive(&pre_bar[s]);
+                    }
+                    __syncwarp();
+                    ++bi;
+                    progressed = true;
+                }
+            }
+            if (!progressed) {
+                if (++idle > UKM_WATCHDOG_SPINS) {
+                    if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+                    break;
+                }
+            } else {
+                idle = 0;
+            }
+        }
+        return;
+    }
+
+    // ================= consumers =================
+    const int tid = (int)threadIdx.x - 32;
+    for (int i = 0; i <= n_my; ++i) {
+        unsigned emitmask = 0;
+        uint64_t outk[VT + 1];
+        unsigned off = 0;
+        uint64_t* slot = nullptr;
+        if (i < n_my) {
+            const int s = i % SLOTS, u = i / SLOTS;
+            slot = s_slots + (size_t)s * SLOT;
+            if (!mbar_wait(&full_bar[s], (unsigned)u & 1u)) {
+                if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+            }
+            const PipeGeom g = s_geom[s];
+            const int na = g.na, nb = g.nb;
+            const uint64_t* sA = slot + g.hA;
+            const uint64_t* sB = slot + g.offB;
+            const int total = na + nb;
+            {
+                int diag = tid * VT;
+                if (diag > total) diag = total;
+                int a = merge_path(sA, na, sB, nb, diag);
+                int b = diag - a;
+                if (OP != OP_MERGE) {
+                    if (a > 0 && b < nb && sA[a - 1] == sB[b]) ++b;
+                }
+                s_part[tid] = (a << 16) | b;
+                if (tid == 0) s_part[NT] = (na << 16) | nb;
+            }
+            named_bar_sync(1, NT);
+            int ai = s_part[tid] >> 16, bi = s_part[tid] & 0xffff;
+            const int a1 = s_part[tid + 1] >> 16, b1 = s_part[tid + 1] & 0xffff;
+            uint64_t ka = sA[ai], kb = sB[bi];
+#pragma unroll
+            for (int it = 0; it <= VT; ++it) {
+                const bool pa = ai < a1, pb = bi < b1;
+                const bool gt = ka > kb;
+                const bool takeA = pa && (!pb || !gt);
+                const bool takeB = pb && !takeA;
+                const bool eq = takeA && pb && (ka == kb);
+                bool emit;
+                if (OP == OP_INTER) emit = eq;
+                else if (OP == OP_DIFF) emit = takeA && !eq;
+                else emit = takeA || takeB;
+                outk[it] = (OP == OP_INTER || OP == OP_DIFF) ? ka : (takeA ? ka : kb);
+                emitmask |= (emit ? 1u : 0u) << it;
+                if (takeA) ka = sA[++ai];
+                if (takeB || (eq && OP != OP_MERGE)) kb = sB[++bi];
+            }
+            unsigned tile_total;
+            off = group_excl_scan_u32<NT>((unsigned)__popc(emitmask), (unsigned)tid, s_scan, &tile_total, 1);
+            // every consumer is past its walk (two barriers inside the scan): the slot may be overwritten
+            if (tid == 0) {
+                s_cnt[s] = tile_total;
+                if (OP != OP_MERGE) {
+                    const int tile = (int)blockIdx.x + i * G;
+                    if (tile > 0) st_relaxed_u64(&p.status[tile], UKM_LB_PARTIAL | (uint64_t)tile_total);
+                    mbar_arrive(&cnt_bar[s]);  // release: s_cnt visible to the producer warp
+                }
+            }
+        }
+        // copy the previous tile out while this tile's count travels
+        if (i > 0) {
+            const int sp = (i - 1) % SLOTS, up = (i - 1) / SLOTS;
+            const uint64_t* prev = s_slots + (size_t)sp * SLOT;
+            unsigned long long prefix;
+            if (OP == OP_MERGE) {
+                prefix = (unsigned long long)s_geom[sp].base;
+                if (tid == 0 && (int)blockIdx.x + (i - 1) * G == p.num_tiles - 1) *p.total_out = prefix + s_cnt[sp];
+            } else {
+                if (!mbar_wait(&pre_bar[sp], (unsigned)up & 1u)) {
+                    if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+                }
+                prefix = s_pre[sp];
+            }
+            const unsigned n_prev = (unsigned)s_cnt[sp];
+            uint64_t* dst = p.outK + prefix;
+            for (unsigned j = tid; j < n_prev; j += NT) dst[j] = prev[j];
+            mbar_arrive(&empty_bar[sp]);  // release: my reads of the slot are done
+        }
+        // stage this tile's outputs in place (after the copy-out so that it overlaps the look-back)
+        if (i < n_my) {
+            unsigned o = off;
+#pragma unroll
+            for (int it = 0; it <= VT; ++it) {
+                if (emitmask & (1u << it)) slot[o++] = outk[it];
+            }
+            named_bar_sync(1, NT);  // staged tile visible to every consumer before the next copy-out
+        }
+    }
+}
+
 // ---- search path for skewed pairs (|B| >> |A|): inter / diff -------------------------------------
 // When the running set A is much smaller than the next file B (inter.go / diff.go after a few files),
 // walking all of B is wasted work: every thread looks its A elements up in B's window for the tile
@@ -584,6 +803,50 @@ int launch_fast(ukm_ctx* ctx, int op, const SetopArgs& a) {
     }
 }
 
+template <int OP, int VT, int SLOTS>
+int launch_pipe_v(ukm_ctx* ctx, SetopArgs a) {
+    constexpr size_t smem = (size_t)SLOTS * (SO_THREADS * VT + 8) * 8;
+    auto kern = setop_pipe_kernel<OP, VT, SLOTS>;
+    static int ctas_per_sm = 0;  // per instantiation
+    if (ctas_per_sm == 0) {
+        UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SO_THREADS + 32, smem));
+        if (nb < 1) return ukm_fail(ctx, UKM_E_INTERNAL, "setop_pipe_kernel does not fit on an SM");
+        ctas_per_sm = nb;
+    }
+    // persistent grid: every CTA must be resident (tiles are chained in index order)
+    int grid = ctas_per_sm * ctx->sm_count;
+    if (grid > a.num_tiles) grid = a.num_tiles;
+    kern<<<grid, SO_THREADS + 32, smem, ctx->stream>>>(a);
+    UKM_LAUNCHED(ctx);
+    return UKM_OK;
+}
+
+template <int VT, int SLOTS>
+int launch_pipe(ukm_ctx* ctx, int op, const SetopArgs& a) {
+    switch (op) {
+        case OP_INTER: return launch_pipe_v<OP_INTER, VT, SLOTS>(ctx, a);
+        case OP_DIFF: return launch_pipe_v<OP_DIFF, VT, SLOTS>(ctx, a);
+        case OP_UNION: return launch_pipe_v<OP_UNION, VT, SLOTS>(ctx, a);
+        default: return launch_pipe_v<OP_MERGE, VT, SLOTS>(ctx, a);
+    }
+}
+
+// UKM_SETOP_PIPE = "0" (one tile per CTA kernel), or "<VT>,<SLOTS>" with VT in {11,15}, SLOTS in {3,4}
+void pipe_cfg(int* vt, int* slots) {
+    *vt = 15;
+    *slots = 3;
+    const char* e = getenv("UKM_SETOP_PIPE");
+    if (!e) return;
+    int v = 0, sl = 0;
+    if (sscanf(e, "%d,%d", &v, &sl) >= 1) {
+        if (v == 0) { *vt = 0; return; }
+        if (v == 11 || v == 15) *vt = v;
+        if (sl == 3 || sl == 4) *slots = sl;
+    }
+}
+
 // merged elements per thread of the keys-only kernel; UKM_SETOP_VT overrides for A/B runs
 int fast_vt() {
     const char* e = getenv("UKM_SETOP_VT");
@@ -610,7 +873,10 @@ int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, boo
     const long long skew = search_skew();
     const bool use_search = (op == OP_INTER || op == OP_DIFF) && !cnt && nA > 0 && skew > 0 && nB >= skew * nA;
     const bool use_fast = !use_search && !tax && !cnt;
-    const int vt = fast_vt();
+    int pipe_vt = 0, pipe_slots = 0;
+    pipe_cfg(&pipe_vt, &pipe_slots);
+    const bool use_pipe = use_fast && pipe_vt != 0;
+    const int vt = use_pipe ? pipe_vt : fast_vt();
     const int tile_elems = use_search ? SS_TILE : (use_fast ? SO_THREADS * vt : SO_TILE);
     const int num_tiles = (int)(((use_search ? nA : total) + tile_elems - 1) / tile_elems);
     ukm_tmp tmp(ctx);
@@ -654,7 +920,10 @@ int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, boo
             setop_partition_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(A.k, nA, B.k, nB, num_tiles, tile_elems,
                                                                                          op != OP_MERGE, d_part, ctx->d_err);
             UKM_LAUNCHED(ctx);
-            if (use_fast) {
+            if (use_pipe) {
+                r = (vt == 11) ? (pipe_slots == 4 ? launch_pipe<11, 4>(ctx, op, a) : launch_pipe<11, 3>(ctx, op, a))
+                               : (pipe_slots == 4 ? launch_pipe<15, 4>(ctx, op, a) : launch_pipe<15, 3>(ctx, op, a));
+            } else if (use_fast) {
                 r = vt == 11 ? launch_fast<11>(ctx, op, a) : vt == 19 ? launch_fast<19>(ctx, op, a)
                   : vt == 23 ? launch_fast<23>(ctx, op, a) : launch_fast<15>(ctx, op, a);
             } else {
