@@ -451,7 +451,7 @@ __device__ __forceinline__ unsigned group_excl_scan_u32(unsigned v, unsigned tid
 __device__ __forceinline__ uint64_t tile_exclusive_prefix(uint64_t* status, int tile, uint64_t tile_total, int* err,
                                                           unsigned long long* s_prefix) {
     if (threadIdx.x < 32) {
-        uint64_t pre = lookback_wide(status, tile, tile_total, true, err);
+        uint64_t pre = lookback_warp(status, tile, tile_total, err);
         if (threadIdx.x == 0) *s_prefix = pre;
     }
     __syncthreads();

@@ -433,29 +433,36 @@ __global__ void __launch_bounds__(SO_THREADS, (VT <= 15 ? 3 : 2)) setop_fast_ker
 
 
 // ---- persistent, warp-specialised pipeline (keys-only) ----------------------------------------------
-// One producer warp + SO_THREADS consumer threads per CTA, CTAs resident for the whole launch, tiles
-// taken round-robin (tile = blockIdx.x + i * gridDim.x).  A ring of SLOTS shared-memory tile slots:
-//   producer : waits for a free slot, reads the tile geometry, issues the two TMA bulk loads
-//              (full[s] mbarrier), and -- off the consumers' critical path -- chains the tile's output
-//              count to its predecessors (decoupled look-back) and posts the prefix (pre[s]).
-//   consumers: wait full[s]; merge-path search; three-way walk; scan; stage the outputs IN PLACE in the
-//              slot; post the count (cnt[s]); then copy the PREVIOUS tile out (its prefix has had a whole
-//              tile's worth of time to arrive) and hand its slot back (empty[s]).
-// Global-memory latency (geometry, TMA, look-back) never stalls the merging warps.
+// CTAs stay resident for the whole launch and take tiles round-robin (tile = blockIdx.x + i*gridDim.x), so
+// "iteration i" of the grid covers the contiguous tile block [i*G, (i+1)*G).  Warp roles:
+//   warp 0  loader : waits for a free slot of the shared-memory ring, reads the tile geometry, issues the
+//                    two TMA bulk loads (full[s] mbarrier).
+//   warp 1  prefix : output offsets.  Instead of a chained look-back (measured: 60% of the kernel when the
+//                    count is only known at the END of a tile's work), every CTA gathers the G counts of
+//                    the iteration in ONE round of independent loads: prefix = P_i + sum of counts of lower
+//                    CTAs, P_{i+1} = P_i + sum of all counts.  Posts it through pre[s].
+//   warps 2+ consumers: wait full[s]; merge-path search; three-way walk; scan; publish the count; copy tile
+//                    i-DEFER out (its prefix has had DEFER tile-times to arrive) and free its slot; stage
+//                    this tile's outputs IN PLACE in its slot.
+// Global-memory latency (geometry, TMA, counts of other CTAs) never stalls the merging warps.
+constexpr int PIPE_MAX_GRID = 384;  // prefix warp keeps PIPE_MAX_GRID/32 counts per lane
+constexpr int PIPE_AUX = 64;        // loader + prefix warps
+
 struct PipeGeom {
     long long base;  // a_lo + b_lo (merged rank of the tile start)
     int na, nb, hA, offB;
 };
 
 template <int OP, int VT, int SLOTS>
-__global__ void __launch_bounds__(SO_THREADS + 32, 2) setop_pipe_kernel(const SetopArgs p) {
+__global__ void __launch_bounds__(SO_THREADS + PIPE_AUX, 2) setop_pipe_kernel(const SetopArgs p) {
     constexpr int NT = SO_THREADS;  // consumer threads
     constexpr int T = NT * VT;
     constexpr int SLOT = T + 8;
     constexpr int NW = NT / 32;
+    constexpr int DEFER = SLOTS - 2;  // copy-out lag in tiles
     extern __shared__ __align__(16) unsigned char so_smem[];
     uint64_t* s_slots = reinterpret_cast<uint64_t*>(so_smem);  // SLOTS * SLOT
-    __shared__ __align__(8) uint64_t full_bar[SLOTS], empty_bar[SLOTS], cnt_bar[SLOTS], pre_bar[SLOTS];
+    __shared__ __align__(8) uint64_t full_bar[SLOTS], empty_bar[SLOTS], pre_bar[SLOTS];
     __shared__ unsigned long long s_cnt[SLOTS], s_pre[SLOTS];
     __shared__ PipeGeom s_geom[SLOTS];
     __shared__ int s_part[NT + 1];
@@ -467,79 +474,103 @@ __global__ void __launch_bounds__(SO_THREADS + 32, 2) setop_pipe_kernel(const Se
         for (int s = 0; s < SLOTS; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], NT);  // every consumer thread arrives after its share of the copy-out
-            mbar_init(&cnt_bar[s], 1);
             mbar_init(&pre_bar[s], 1);
         }
         mbar_fence_init();
     }
     __syncthreads();
+    const unsigned lane = lane_id();
 
     if (threadIdx.x < 32) {
-        // ================= producer / look-back warp =================
-        const unsigned lane = threadIdx.x;
-        int li = 0, bi = 0;  // next tile (local index) to load / to chain
-        unsigned idle = 0;
-        while (li < n_my || (OP != OP_MERGE && bi < n_my)) {
-            bool progressed = false;
-            if (li < n_my) {
-                const int s = li % SLOTS, u = li / SLOTS;
-                const bool slot_free = (u == 0) || mbar_try_wait(&empty_bar[s], (unsigned)(u - 1) & 1u);
-                if (slot_free) {
-                    if (lane == 0) {
-                        const int tile = (int)blockIdx.x + li * G;
-                        const long long a_lo = p.part[2 * tile], b_lo = p.part[2 * tile + 1];
-                        const int na = (int)(p.part[2 * tile + 2] - a_lo), nb = (int)(p.part[2 * tile + 3] - b_lo);
-                        const int hA = slice_offset(p.A, a_lo), hB = slice_offset(p.B, b_lo);
-                        const int offB = ((hA + na + 1) & ~1) + hB;
-                        uint64_t* slot = s_slots + (size_t)s * SLOT;
-                        PipeGeom g;
-                        g.base = a_lo + b_lo;
-                        g.na = na; g.nb = nb; g.hA = hA; g.offB = offB;
-                        s_geom[s] = g;
-                        // head/tail elements by plain stores, bodies by TMA; the arrive (release) publishes both
-                        const unsigned bytes = slice_body_bytes(p.A, a_lo, na) + slice_body_bytes(p.B, b_lo, nb);
-                        slice_issue_plain(slot, p.A, a_lo, na);
-                        slice_issue_plain(slot + offB - hB, p.B, b_lo, nb);
-                        mbar_expect_tx(&full_bar[s], bytes);
-                        slice_issue_bulk(slot, p.A, a_lo, na, &full_bar[s]);
-                        slice_issue_bulk(slot + offB - hB, p.B, b_lo, nb, &full_bar[s]);
-                    }
-                    __syncwarp();
-                    ++li;
-                    progressed = true;
-                }
+        // ================= loader warp =================
+        for (int li = 0; li < n_my; ++li) {
+            const int s = li % SLOTS, u = li / SLOTS;
+            if (u > 0 && !mbar_wait(&empty_bar[s], (unsigned)(u - 1) & 1u)) {
+                if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
             }
-            if (OP != OP_MERGE && bi < li) {
-                const int s = bi % SLOTS, u = bi / SLOTS;
-                if (mbar_try_wait(&cnt_bar[s], (unsigned)u & 1u)) {
-                    const int tile = (int)blockIdx.x + bi * G;
-                    const unsigned long long total = s_cnt[s];
-                    const unsigned long long prefix = lookback_wide(p.status, tile, total, false, p.err);
-                    if (lane == 0) {
-                        s_pre[s] = prefix;
-                        if (tile == p.num_tiles - 1) *p.total_out = prefix + total;
-                        mbar_arrive(&pre_bar[s]);
-                    }
-                    __syncwarp();
-                    ++bi;
-                    progressed = true;
-                }
+            if (lane == 0) {
+                const int tile = (int)blockIdx.x + li * G;
+                const long long a_lo = p.part[2 * tile], b_lo = p.part[2 * tile + 1];
+                const int na = (int)(p.part[2 * tile + 2] - a_lo), nb = (int)(p.part[2 * tile + 3] - b_lo);
+                const int hA = slice_offset(p.A, a_lo), hB = slice_offset(p.B, b_lo);
+                const int offB = ((hA + na + 1) & ~1) + hB;
+                uint64_t* slot = s_slots + (size_t)s * SLOT;
+                PipeGeom g;
+                g.base = a_lo + b_lo;
+                g.na = na; g.nb = nb; g.hA = hA; g.offB = offB;
+                s_geom[s] = g;
+                // head/tail elements by plain stores, bodies by TMA; the arrive (release) publishes both
+                const unsigned bytes = slice_body_bytes(p.A, a_lo, na) + slice_body_bytes(p.B, b_lo, nb);
+                slice_issue_plain(slot, p.A, a_lo, na);
+                slice_issue_plain(slot + offB - hB, p.B, b_lo, nb);
+                mbar_expect_tx(&full_bar[s], bytes);
+                slice_issue_bulk(slot, p.A, a_lo, na, &full_bar[s]);
+                slice_issue_bulk(slot + offB - hB, p.B, b_lo, nb, &full_bar[s]);
             }
-            if (!progressed) {
-                if (++idle > UKM_WATCHDOG_SPINS) {
+            __syncwarp();
+        }
+        return;
+    }
+    if (threadIdx.x < 64) {
+        // ================= prefix warp =================
+        if (OP == OP_MERGE) return;  // positions are data independent
+        constexpr int MAXM = PIPE_MAX_GRID / 32;
+        unsigned long long P = 0;  // outputs of all earlier iterations (identical on every CTA)
+        for (int bi = 0; bi < n_my; ++bi) {
+            const int s = bi % SLOTS, u = bi / SLOTS;
+            const int tile0 = bi * G;
+            const int n_iter = (p.num_tiles - tile0) < G ? (p.num_tiles - tile0) : G;  // tiles in this iteration
+            unsigned long long val[MAXM];
+            unsigned have = 0;  // bit m: val[m] arrived
+            unsigned spins = 0;
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) {
+                val[m] = 0;
+                if ((int)lane + 32 * m >= n_iter) have |= 1u << m;
+            }
+            while (true) {
+#pragma unroll
+                for (int m = 0; m < MAXM; ++m) {
+                    if (!(have & (1u << m))) {
+                        const uint64_t w = ld_relaxed_u64(&p.status[tile0 + (int)lane + 32 * m]);
+                        if (w >> 62) {
+                            val[m] = UKM_LB_VALUE(w);
+                            have |= 1u << m;
+                        }
+                    }
+                }
+                if (__all_sync(0xffffffffu, have == ((1u << MAXM) - 1))) break;
+                if (++spins > UKM_WATCHDOG_SPINS) {
                     if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
                     break;
                 }
-            } else {
-                idle = 0;
             }
+            unsigned long long before = 0, all = 0;
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) {
+                all += val[m];
+                if ((int)lane + 32 * m < (int)blockIdx.x) before += val[m];
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                before += __shfl_xor_sync(0xffffffffu, before, d);
+                all += __shfl_xor_sync(0xffffffffu, all, d);
+            }
+            if (lane == 0) {
+                s_pre[s] = P + before;
+                if (tile0 + n_iter == p.num_tiles && (int)blockIdx.x == n_iter - 1) *p.total_out = P + all;
+                mbar_arrive(&pre_bar[s]);
+            }
+            P += all;
+            (void)u;
+            __syncwarp();
         }
         return;
     }
 
     // ================= consumers =================
-    const int tid = (int)threadIdx.x - 32;
-    for (int i = 0; i <= n_my; ++i) {
+    const int tid = (int)threadIdx.x - PIPE_AUX;
+    for (int i = 0; i < n_my + DEFER; ++i) {
         unsigned emitmask = 0;
         uint64_t outk[VT + 1];
         unsigned off = 0;
@@ -591,21 +622,18 @@ __global__ void __launch_bounds__(SO_THREADS + 32, 2) setop_pipe_kernel(const Se
             // every consumer is past its walk (two barriers inside the scan): the slot may be overwritten
             if (tid == 0) {
                 s_cnt[s] = tile_total;
-                if (OP != OP_MERGE) {
-                    const int tile = (int)blockIdx.x + i * G;
-                    if (tile > 0) st_relaxed_u64(&p.status[tile], UKM_LB_PARTIAL | (uint64_t)tile_total);
-                    mbar_arrive(&cnt_bar[s]);  // release: s_cnt visible to the producer warp
-                }
+                if (OP != OP_MERGE) st_relaxed_u64(&p.status[(int)blockIdx.x + i * G], UKM_LB_PARTIAL | (uint64_t)tile_total);
             }
         }
-        // copy the previous tile out while this tile's count travels
-        if (i > 0) {
-            const int sp = (i - 1) % SLOTS, up = (i - 1) / SLOTS;
+        // copy tile i-DEFER out while this tile's count travels
+        if (i >= DEFER && i - DEFER < n_my) {
+            const int ip = i - DEFER;
+            const int sp = ip % SLOTS, up = ip / SLOTS;
             const uint64_t* prev = s_slots + (size_t)sp * SLOT;
             unsigned long long prefix;
             if (OP == OP_MERGE) {
                 prefix = (unsigned long long)s_geom[sp].base;
-                if (tid == 0 && (int)blockIdx.x + (i - 1) * G == p.num_tiles - 1) *p.total_out = prefix + s_cnt[sp];
+                if (tid == 0 && (int)blockIdx.x + ip * G == p.num_tiles - 1) *p.total_out = prefix + s_cnt[sp];
             } else {
                 if (!mbar_wait(&pre_bar[sp], (unsigned)up & 1u)) {
                     if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
@@ -617,15 +645,15 @@ __global__ void __launch_bounds__(SO_THREADS + 32, 2) setop_pipe_kernel(const Se
             for (unsigned j = tid; j < n_prev; j += NT) dst[j] = prev[j];
             mbar_arrive(&empty_bar[sp]);  // release: my reads of the slot are done
         }
-        // stage this tile's outputs in place (after the copy-out so that it overlaps the look-back)
+        // stage this tile's outputs in place
         if (i < n_my) {
             unsigned o = off;
 #pragma unroll
             for (int it = 0; it <= VT; ++it) {
                 if (emitmask & (1u << it)) slot[o++] = outk[it];
             }
-            named_bar_sync(1, NT);  // staged tile visible to every consumer before the next copy-out
         }
+        named_bar_sync(1, NT);  // staged tile (and s_cnt) visible to every consumer before a later copy-out
     }
 }
 
@@ -811,14 +839,15 @@ int launch_pipe_v(ukm_ctx* ctx, SetopArgs a) {
     if (ctas_per_sm == 0) {
         UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SO_THREADS + 32, smem));
+        UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SO_THREADS + PIPE_AUX, smem));
         if (nb < 1) return ukm_fail(ctx, UKM_E_INTERNAL, "setop_pipe_kernel does not fit on an SM");
         ctas_per_sm = nb;
     }
     // persistent grid: every CTA must be resident (tiles are chained in index order)
     int grid = ctas_per_sm * ctx->sm_count;
+    if (grid > PIPE_MAX_GRID) grid = PIPE_MAX_GRID;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    kern<<<grid, SO_THREADS + 32, smem, ctx->stream>>>(a);
+    kern<<<grid, SO_THREADS + PIPE_AUX, smem, ctx->stream>>>(a);
     UKM_LAUNCHED(ctx);
     return UKM_OK;
 }
