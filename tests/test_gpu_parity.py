@@ -193,7 +193,7 @@ def member_files(N, nfiles, S=3, T=4):
     return [oracle.member_file(0, N, N, S, T, f) for f in range(nfiles)]
 
 
-@pytest.mark.parametrize("kernel", ["pipe:15,3", "pipe:11,4", "pipe:11,3", "pipe:15,4", "vt:11", "vt:15", "vt:19", "vt:23"])
+@pytest.mark.parametrize("kernel", ["pipe:15,3", "pipe:13,4", "pipe:11,4", "pipe:11,3", "pipe:9,5", "vt:11", "vt:15", "vt:19", "vt:23"])
 @pytest.mark.parametrize("skew", ["0", "3"])
 def test_setop_kernel_variants(eng, kernel, skew, monkeypatch):
     """Every shape of the keys-only kernels (persistent pipeline / one tile per CTA), with and without

@@ -453,8 +453,8 @@ struct PipeGeom {
     int na, nb, hA, offB;
 };
 
-template <int OP, int VT, int SLOTS>
-__global__ void __launch_bounds__(SO_THREADS + PIPE_AUX, 2) setop_pipe_kernel(const SetopArgs p) {
+template <int OP, int VT, int SLOTS, int MINB>
+__global__ void __launch_bounds__(SO_THREADS + PIPE_AUX, MINB) setop_pipe_kernel(const SetopArgs p) {
     constexpr int NT = SO_THREADS;  // consumer threads
     constexpr int T = NT * VT;
     constexpr int SLOT = T + 8;
@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(SO_THREADS + PIPE_AUX, 2) setop_pipe_kernel(co
                     }
                 }
                 if (__all_sync(0xffffffffu, have == ((1u << MAXM) - 1))) break;
+                __nanosleep(100);  // do not steal issue slots from the merging warps while other CTAs catch up
                 if (++spins > UKM_WATCHDOG_SPINS) {
                     if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
                     break;
@@ -831,10 +832,10 @@ int launch_fast(ukm_ctx* ctx, int op, const SetopArgs& a) {
     }
 }
 
-template <int OP, int VT, int SLOTS>
+template <int OP, int VT, int SLOTS, int MINB>
 int launch_pipe_v(ukm_ctx* ctx, SetopArgs a) {
     constexpr size_t smem = (size_t)SLOTS * (SO_THREADS * VT + 8) * 8;
-    auto kern = setop_pipe_kernel<OP, VT, SLOTS>;
+    auto kern = setop_pipe_kernel<OP, VT, SLOTS, MINB>;
     static int ctas_per_sm = 0;  // per instantiation
     if (ctas_per_sm == 0) {
         UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -852,17 +853,17 @@ int launch_pipe_v(ukm_ctx* ctx, SetopArgs a) {
     return UKM_OK;
 }
 
-template <int VT, int SLOTS>
+template <int VT, int SLOTS, int MINB>
 int launch_pipe(ukm_ctx* ctx, int op, const SetopArgs& a) {
     switch (op) {
-        case OP_INTER: return launch_pipe_v<OP_INTER, VT, SLOTS>(ctx, a);
-        case OP_DIFF: return launch_pipe_v<OP_DIFF, VT, SLOTS>(ctx, a);
-        case OP_UNION: return launch_pipe_v<OP_UNION, VT, SLOTS>(ctx, a);
-        default: return launch_pipe_v<OP_MERGE, VT, SLOTS>(ctx, a);
+        case OP_INTER: return launch_pipe_v<OP_INTER, VT, SLOTS, MINB>(ctx, a);
+        case OP_DIFF: return launch_pipe_v<OP_DIFF, VT, SLOTS, MINB>(ctx, a);
+        case OP_UNION: return launch_pipe_v<OP_UNION, VT, SLOTS, MINB>(ctx, a);
+        default: return launch_pipe_v<OP_MERGE, VT, SLOTS, MINB>(ctx, a);
     }
 }
 
-// UKM_SETOP_PIPE = "0" (one tile per CTA kernel), or "<VT>,<SLOTS>" with VT in {11,15}, SLOTS in {3,4}
+// UKM_SETOP_PIPE = "0" (one tile per CTA kernel) or "<VT>,<SLOTS>": one of 15,3  13,4  11,4  11,3  9,5
 void pipe_cfg(int* vt, int* slots) {
     *vt = 15;
     *slots = 3;
@@ -871,8 +872,10 @@ void pipe_cfg(int* vt, int* slots) {
     int v = 0, sl = 0;
     if (sscanf(e, "%d,%d", &v, &sl) >= 1) {
         if (v == 0) { *vt = 0; return; }
-        if (v == 11 || v == 15) *vt = v;
-        if (sl == 3 || sl == 4) *slots = sl;
+        if ((v == 15 && sl == 3) || (v == 13 && sl == 4) || (v == 11 && (sl == 3 || sl == 4)) || (v == 9 && sl == 5)) {
+            *vt = v;
+            *slots = sl;
+        }
     }
 }
 
@@ -950,8 +953,11 @@ int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, boo
                                                                                          op != OP_MERGE, d_part, ctx->d_err);
             UKM_LAUNCHED(ctx);
             if (use_pipe) {
-                r = (vt == 11) ? (pipe_slots == 4 ? launch_pipe<11, 4>(ctx, op, a) : launch_pipe<11, 3>(ctx, op, a))
-                               : (pipe_slots == 4 ? launch_pipe<15, 4>(ctx, op, a) : launch_pipe<15, 3>(ctx, op, a));
+                if (vt == 13) r = launch_pipe<13, 4, 2>(ctx, op, a);
+                else if (vt == 11 && pipe_slots == 4) r = launch_pipe<11, 4, 2>(ctx, op, a);
+                else if (vt == 11) r = launch_pipe<11, 3, 3>(ctx, op, a);  // 3 CTAs/SM: 68 KB each, <= 68 registers
+                else if (vt == 9) r = launch_pipe<9, 5, 2>(ctx, op, a);
+                else r = launch_pipe<15, 3, 2>(ctx, op, a);
             } else if (use_fast) {
                 r = vt == 11 ? launch_fast<11>(ctx, op, a) : vt == 19 ? launch_fast<19>(ctx, op, a)
                   : vt == 23 ? launch_fast<23>(ctx, op, a) : launch_fast<15>(ctx, op, a);
