@@ -193,13 +193,13 @@ def member_files(N, nfiles, S=3, T=4):
     return [oracle.member_file(0, N, N, S, T, f) for f in range(nfiles)]
 
 
-@pytest.mark.parametrize("kernel", ["pipe:15,3", "pipe:13,4", "pipe:11,4", "pipe:11,3", "pipe:9,5", "vt:11", "vt:15", "vt:19", "vt:23"])
+@pytest.mark.parametrize("kernel", ["pipe:0", "pipe:1", "pipe:2", "pipe:3", "pipe:4", "pipe:5", "vt:11", "vt:15", "vt:19", "vt:23"])
 @pytest.mark.parametrize("skew", ["0", "3"])
 def test_setop_kernel_variants(eng, kernel, skew, monkeypatch):
     """Every shape of the keys-only kernels (persistent pipeline / one tile per CTA), with and without
     the search path for skewed pairs."""
     kind, cfg = kernel.split(":")
-    monkeypatch.setenv("UKM_SETOP_PIPE", cfg if kind == "pipe" else "0")
+    monkeypatch.setenv("UKM_SETOP_PIPE", cfg if kind == "pipe" else "off")
     if kind == "vt":
         monkeypatch.setenv("UKM_SETOP_VT", cfg)
     monkeypatch.setenv("UKM_SETOP_SKEW", skew)

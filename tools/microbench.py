@@ -63,7 +63,7 @@ def main():
             U = n
             files = [eng.synth_member_file(0, U, U, 3, 4, f).clone() for f in range(8)]
             tot = sum(int(f.shape[0]) for f in files)
-            for pipe, vt, skew in [("15,3", "15", "3"), ("13,4", "15", "3"), ("11,4", "15", "3"), ("11,3", "15", "3"), ("9,5", "15", "3")]:
+            for pipe, vt, skew in [("0", "15", "3"), ("1", "15", "3"), ("2", "15", "3"), ("3", "15", "3"), ("4", "15", "3"), ("5", "15", "3")]:
                 os.environ["UKM_SETOP_PIPE"], os.environ["UKM_SETOP_VT"], os.environ["UKM_SETOP_SKEW"] = pipe, vt, skew
                 res = {}
                 for name in ("inter", "diff", "union"):

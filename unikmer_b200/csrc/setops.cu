@@ -453,9 +453,8 @@ struct PipeGeom {
     int na, nb, hA, offB;
 };
 
-template <int OP, int VT, int SLOTS, int MINB>
-__global__ void __launch_bounds__(SO_THREADS + PIPE_AUX, MINB) setop_pipe_kernel(const SetopArgs p) {
-    constexpr int NT = SO_THREADS;  // consumer threads
+template <int OP, int NT, int VT, int SLOTS, int MINB>  // NT = consumer threads
+__global__ void __launch_bounds__(NT + PIPE_AUX, MINB) setop_pipe_kernel(const SetopArgs p) {
     constexpr int T = NT * VT;
     constexpr int SLOT = T + 8;
     constexpr int NW = NT / 32;
@@ -832,15 +831,15 @@ int launch_fast(ukm_ctx* ctx, int op, const SetopArgs& a) {
     }
 }
 
-template <int OP, int VT, int SLOTS, int MINB>
+template <int OP, int NT, int VT, int SLOTS, int MINB>
 int launch_pipe_v(ukm_ctx* ctx, SetopArgs a) {
-    constexpr size_t smem = (size_t)SLOTS * (SO_THREADS * VT + 8) * 8;
-    auto kern = setop_pipe_kernel<OP, VT, SLOTS, MINB>;
+    constexpr size_t smem = (size_t)SLOTS * (NT * VT + 8) * 8;
+    auto kern = setop_pipe_kernel<OP, NT, VT, SLOTS, MINB>;
     static int ctas_per_sm = 0;  // per instantiation
     if (ctas_per_sm == 0) {
         UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SO_THREADS + PIPE_AUX, smem));
+        UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT + PIPE_AUX, smem));
         if (nb < 1) return ukm_fail(ctx, UKM_E_INTERNAL, "setop_pipe_kernel does not fit on an SM");
         ctas_per_sm = nb;
     }
@@ -848,35 +847,34 @@ int launch_pipe_v(ukm_ctx* ctx, SetopArgs a) {
     int grid = ctas_per_sm * ctx->sm_count;
     if (grid > PIPE_MAX_GRID) grid = PIPE_MAX_GRID;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    kern<<<grid, SO_THREADS + PIPE_AUX, smem, ctx->stream>>>(a);
+    kern<<<grid, NT + PIPE_AUX, smem, ctx->stream>>>(a);
     UKM_LAUNCHED(ctx);
     return UKM_OK;
 }
 
-template <int VT, int SLOTS, int MINB>
+template <int NT, int VT, int SLOTS, int MINB>
 int launch_pipe(ukm_ctx* ctx, int op, const SetopArgs& a) {
     switch (op) {
-        case OP_INTER: return launch_pipe_v<OP_INTER, VT, SLOTS, MINB>(ctx, a);
-        case OP_DIFF: return launch_pipe_v<OP_DIFF, VT, SLOTS, MINB>(ctx, a);
-        case OP_UNION: return launch_pipe_v<OP_UNION, VT, SLOTS, MINB>(ctx, a);
-        default: return launch_pipe_v<OP_MERGE, VT, SLOTS, MINB>(ctx, a);
+        case OP_INTER: return launch_pipe_v<OP_INTER, NT, VT, SLOTS, MINB>(ctx, a);
+        case OP_DIFF: return launch_pipe_v<OP_DIFF, NT, VT, SLOTS, MINB>(ctx, a);
+        case OP_UNION: return launch_pipe_v<OP_UNION, NT, VT, SLOTS, MINB>(ctx, a);
+        default: return launch_pipe_v<OP_MERGE, NT, VT, SLOTS, MINB>(ctx, a);
     }
 }
 
-// UKM_SETOP_PIPE = "0" (one tile per CTA kernel) or "<VT>,<SLOTS>": one of 15,3  13,4  11,4  11,3  9,5
-void pipe_cfg(int* vt, int* slots) {
-    *vt = 15;
-    *slots = 3;
+// Pipeline shapes: consumer threads x elements per thread x ring slots.  UKM_SETOP_PIPE picks one by
+// index for A/B runs ("off" = the one-tile-per-CTA kernel).
+struct PipeCfg {
+    int nt, vt, slots;
+};
+const PipeCfg kPipeCfgs[] = {{256, 15, 3}, {256, 13, 4}, {384, 10, 3}, {384, 11, 3}, {512, 7, 3}, {256, 11, 4}};
+constexpr int kNumPipeCfgs = 6;
+int pipe_cfg() {  // -1 = off
     const char* e = getenv("UKM_SETOP_PIPE");
-    if (!e) return;
-    int v = 0, sl = 0;
-    if (sscanf(e, "%d,%d", &v, &sl) >= 1) {
-        if (v == 0) { *vt = 0; return; }
-        if ((v == 15 && sl == 3) || (v == 13 && sl == 4) || (v == 11 && (sl == 3 || sl == 4)) || (v == 9 && sl == 5)) {
-            *vt = v;
-            *slots = sl;
-        }
-    }
+    if (!e) return 0;
+    if (e[0] == 'o') return -1;
+    int v = atoi(e);
+    return (v >= 0 && v < kNumPipeCfgs) ? v : 0;
 }
 
 // merged elements per thread of the keys-only kernel; UKM_SETOP_VT overrides for A/B runs
@@ -905,11 +903,12 @@ int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, boo
     const long long skew = search_skew();
     const bool use_search = (op == OP_INTER || op == OP_DIFF) && !cnt && nA > 0 && skew > 0 && nB >= skew * nA;
     const bool use_fast = !use_search && !tax && !cnt;
-    int pipe_vt = 0, pipe_slots = 0;
-    pipe_cfg(&pipe_vt, &pipe_slots);
-    const bool use_pipe = use_fast && pipe_vt != 0;
-    const int vt = use_pipe ? pipe_vt : fast_vt();
-    const int tile_elems = use_search ? SS_TILE : (use_fast ? SO_THREADS * vt : SO_TILE);
+    const int pc = pipe_cfg();
+    const bool use_pipe = use_fast && pc >= 0;
+    const int vt = fast_vt();
+    const int tile_elems = use_search ? SS_TILE
+                         : use_pipe ? kPipeCfgs[pc].nt * kPipeCfgs[pc].vt
+                         : use_fast ? SO_THREADS * vt : SO_TILE;
     const int num_tiles = (int)(((use_search ? nA : total) + tile_elems - 1) / tile_elems);
     ukm_tmp tmp(ctx);
     long long* d_part = nullptr;
@@ -953,11 +952,14 @@ int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, boo
                                                                                          op != OP_MERGE, d_part, ctx->d_err);
             UKM_LAUNCHED(ctx);
             if (use_pipe) {
-                if (vt == 13) r = launch_pipe<13, 4, 2>(ctx, op, a);
-                else if (vt == 11 && pipe_slots == 4) r = launch_pipe<11, 4, 2>(ctx, op, a);
-                else if (vt == 11) r = launch_pipe<11, 3, 3>(ctx, op, a);  // 3 CTAs/SM: 68 KB each, <= 68 registers
-                else if (vt == 9) r = launch_pipe<9, 5, 2>(ctx, op, a);
-                else r = launch_pipe<15, 3, 2>(ctx, op, a);
+                switch (pc) {
+                    case 1: r = launch_pipe<256, 13, 4, 2>(ctx, op, a); break;
+                    case 2: r = launch_pipe<384, 10, 3, 2>(ctx, op, a); break;
+                    case 3: r = launch_pipe<384, 11, 3, 2>(ctx, op, a); break;
+                    case 4: r = launch_pipe<512, 7, 3, 2>(ctx, op, a); break;
+                    case 5: r = launch_pipe<256, 11, 4, 2>(ctx, op, a); break;
+                    default: r = launch_pipe<256, 15, 3, 2>(ctx, op, a); break;
+                }
             } else if (use_fast) {
                 r = vt == 11 ? launch_fast<11>(ctx, op, a) : vt == 19 ? launch_fast<19>(ctx, op, a)
                   : vt == 23 ? launch_fast<23>(ctx, op, a) : launch_fast<15>(ctx, op, a);
