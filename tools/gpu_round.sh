@@ -2,8 +2,11 @@
 # One GPU-box session: tests, benches, ncu evidence.  Everything lands in gpurun_out/.
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x --timeout=240 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 1200 python tools/microbench.py --what setops > gpurun_out/microbench.jsonl 2> gpurun_out/microbench.err; cat gpurun_out/microbench.jsonl; tail -5 gpurun_out/microbench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > /dev/null 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:setop_pipe_kernel -c 2 -o gpurun_out/setop_prof -f python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > /dev/null 2> gpurun_out/ncu_setop.err; tail -3 gpurun_out/ncu_setop.err
+timeout 900 python -m pytest tests -m gpu -q -x --timeout=300 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; tail -c 3500 gpurun_out/bench_full.json; tail -5 gpurun_out/bench_full.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json; tail -3 gpurun_out/bench_ref.err
+timeout 900 python tools/microbench.py --what sort1,pairs,kmers,count,fold > gpurun_out/microbench.jsonl 2> gpurun_out/microbench.err; cat gpurun_out/microbench.jsonl; tail -5 gpurun_out/microbench.err
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/bench_under_ncu.json 2> gpurun_out/ncu_launches.err; tail -3 gpurun_out/ncu_launches.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:setop_pipe_kernel -s 4 -c 2 -o gpurun_out/setop_union_prof -f python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu > /dev/null 2> gpurun_out/ncu_setop.err; tail -3 gpurun_out/ncu_setop.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:onesweep_kernel -s 2 -c 1 -o gpurun_out/onesweep_prof -f python tools/microbench.py --what sort1 --n 3e8 > /dev/null 2> gpurun_out/ncu_sort.err; tail -3 gpurun_out/ncu_sort.err
 ls -la gpurun_out

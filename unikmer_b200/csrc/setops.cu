@@ -871,7 +871,7 @@ const PipeCfg kPipeCfgs[] = {{256, 15, 3}, {256, 13, 4}, {384, 10, 3}, {384, 11,
 constexpr int kNumPipeCfgs = 6;
 int pipe_cfg() {  // -1 = off
     const char* e = getenv("UKM_SETOP_PIPE");
-    if (!e) return 0;
+    if (!e) return 1;  // 256 x 13, 4 slots: best union time on B200 (profiles/)
     if (e[0] == 'o') return -1;
     int v = atoi(e);
     return (v >= 0 && v < kNumPipeCfgs) ? v : 0;
