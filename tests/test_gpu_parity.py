@@ -510,6 +510,22 @@ def test_iterator_multi_record(eng, hashed, canonical, circular):
          oracle.count(bases, off, k, canonical=canonical, hashed=hashed, circular=circular), "count multi-record")
 
 
+@pytest.mark.parametrize("limit", ["1000000000", "200000", "30000"])
+def test_count_key_range_passes(eng, limit, monkeypatch):
+    """count cuts the code space into key-range passes when the k-mers would not fit (C4); forced here on a
+    small input.  Includes a skewed 2-bit case (poly-A) that overflows a pass buffer and is retried."""
+    monkeypatch.setenv("UKM_COUNT_PASS", limit)
+    recs = [oracle.synth_bases(r_, 0, n, 5) for r_, n in enumerate((300_000, 17, 120_000))]
+    recs.append(np.frombuffer(b"A" * 50_000 + b"ACGT" * 10_000 + b"T" * 30_000, dtype=np.uint8))
+    bases = np.concatenate(recs)
+    off = np.concatenate([[0], np.cumsum([len(r_) for r_ in recs])]).astype(U64)
+    mh = int(float(2**64 - 1) / 7.0)
+    for kw in ({"hashed": True}, {"hashed": False}, {"hashed": True, "scaled": True, "max_hash": mh}, {"hashed": False, "canonical": False}):
+        k = 31 if kw.get("hashed") else 27
+        kw = {"canonical": True, **kw}
+        same(eng.count(bases, off, k, **kw), oracle.count(bases, off, k, **kw), f"count passes={limit} {kw}")
+
+
 def test_illegal_base_is_an_error(eng):
     import unikmer_b200 as ub
     seq = b"ACGTACGTACGTACGTAC*TACGTACGTACGTACGTACGTACGT"

@@ -18,6 +18,10 @@
 // KM_CHUNK consecutive starts, computing the first k-mer of a run from scratch and rolling
 // afterwards.  K-mers never span records; circular records wrap (reads outside the tile go
 // to global memory).
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "select.cuh"
 
@@ -68,15 +72,26 @@ struct KmerArgs {
     int circular;
     uint64_t* out;
     int* err;
+    // FILTER mode (count): keep range_lo <= code <= range_hi only, append in arbitrary order
+    uint64_t range_lo, range_hi;
+    unsigned long long* cursor;  // number of codes appended so far
+    unsigned long long cap;      // capacity of out; codes beyond it are counted but not stored
 };
 
-template <bool HASHED>
+constexpr int KM_STAGE = 256;  // per-warp staging ring of the FILTER mode (flushed 128 codes at a time)
+
+// FILTER = false: every code to out[out_off[r] + position] (record-then-position order).
+// FILTER = true : codes inside [range_lo, range_hi] are compacted warp-wide through a shared-memory ring and
+//                 appended in 1 KB bursts at a global cursor (order is irrelevant: `count` sorts next).
+template <bool HASHED, bool FILTER>
 __global__ void __launch_bounds__(KM_THREADS) kmer_kernel(const KmerArgs p) {
     __shared__ uint8_t s_b[KM_TILE + KM_HALO + 16];
     __shared__ uint8_t s_lut[256];
     __shared__ uint64_t s_seed[4][8];  // [f_in, f_out(rol k), r_in(rol k-1), r_out(ror 1)][class 0..3, 4..7 = 0]
+    __shared__ uint64_t s_stage[FILTER ? (KM_THREADS / 32) * KM_STAGE : 1];
 
     const int tid = threadIdx.x;
+    const unsigned lane = lane_id();
     const size_t B0 = (size_t)blockIdx.x * KM_TILE;
     const size_t tile_end = (B0 + KM_TILE + KM_HALO < p.n_bases) ? B0 + KM_TILE + KM_HALO : p.n_bases;
     const int tile_len = (int)(tile_end - B0);
@@ -94,86 +109,121 @@ __global__ void __launch_bounds__(KM_THREADS) kmer_kernel(const KmerArgs p) {
     }
     __syncthreads();
 
-    size_t b = B0 + (size_t)tid * KM_CHUNK;
-    size_t b_end = b + KM_CHUNK;
+    const size_t b0 = B0 + (size_t)tid * KM_CHUNK;
+    size_t b_end = b0 + KM_CHUNK;
     if (b_end > B0 + KM_TILE) b_end = B0 + KM_TILE;
     if (b_end > p.n_bases) b_end = p.n_bases;
-    if (b >= b_end) return;
+    const bool any = b0 < b_end;
 
-    // record containing b: last r with rec_off[r] <= b
-    size_t lo = 0, hi = p.n_rec;
-    while (lo + 1 < hi) {
-        size_t mid = (lo + hi) >> 1;
-        if (p.rec_off[mid] <= b) lo = mid;
-        else hi = mid;
+    // record containing b0: last r with rec_off[r] <= b0
+    size_t r = 0, rs = 0, re = 0;
+    unsigned long long obase = 0;
+    if (any) {
+        size_t lo = 0, hi = p.n_rec;
+        while (lo + 1 < hi) {
+            size_t mid = (lo + hi) >> 1;
+            if (p.rec_off[mid] <= b0) lo = mid;
+            else hi = mid;
+        }
+        r = lo;
+        rs = p.rec_off[r];
+        re = p.rec_off[r + 1];
+        obase = p.out_off[r];
     }
-    size_t r = lo;
-    size_t rs = p.rec_off[r], re = p.rec_off[r + 1];
-    unsigned long long obase = p.out_off[r];
 
     const int k = p.k;
     const uint64_t kmask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
     uint64_t fw = 0, rv = 0;
     bool have = false;
     bool illegal = false;
+    uint64_t* stage = s_stage + (FILTER ? (tid >> 5) * KM_STAGE : 0);
+    unsigned staged = 0;  // codes waiting in this warp's ring (warp-uniform)
 
     // base at absolute index q of the current record (q may run past `re` when circular)
     auto fetch = [&](size_t q) -> uint8_t {
         if (q >= re) q = rs + (q - re);
         return (q >= B0 && q < tile_end) ? s_b[q - B0] : p.bases[q];
     };
+    // FILTER: append `n` staged codes (n <= KM_STAGE, warp-uniform) at the global cursor
+    auto flush = [&](unsigned n) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(p.cursor, (unsigned long long)n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (unsigned i = lane; i < n; i += 32)
+            if (base + i < p.cap) p.out[base + i] = stage[i];
+        __syncwarp();
+    };
 
-    for (; b < b_end; ++b) {
-        while (b >= re) {
-            ++r;
-            rs = re;
-            re = p.rec_off[r + 1];
-            obase = p.out_off[r];
-            have = false;
-        }
-        const size_t L = re - rs;
-        if (L < (size_t)k || (!p.circular && b + k > re)) {
-            have = false;
-            continue;
-        }
-        if (!have) {
-            fw = 0;
-            rv = 0;
-            if (HASHED) {
-                for (int i = 0; i < k; ++i) {
-                    uint8_t c = s_lut[fetch(b + i)];
-                    uint64_t sf = c < 4 ? s_seed[0][c] : 0ull;
-                    uint64_t sr = c < 4 ? s_seed[0][3 - c] : 0ull;
-                    fw ^= rol64d(sf, (unsigned)(k - 1 - i));
-                    rv ^= rol64d(sr, (unsigned)i);
-                }
-            } else {
-                for (int i = 0; i < k; ++i) {
-                    uint8_t c = s_lut[fetch(b + i)];
-                    if (c == 255) illegal = true;
-                    uint64_t v = (c >= 4 ? (uint64_t)(c - 4) : (uint64_t)c) & 3u;
-                    fw = ((fw << 2) | v) & kmask;
-                    rv = (rv >> 2) | ((v ^ 3u) << (2 * (k - 1)));
-                }
+    for (int j = 0; j < KM_CHUNK; ++j) {  // uniform trip count: the FILTER mode votes warp-wide every step
+        const size_t b = b0 + (size_t)j;
+        bool emit = false;
+        uint64_t code = 0;
+        if (b < b_end) {
+            while (b >= re) {
+                ++r;
+                rs = re;
+                re = p.rec_off[r + 1];
+                obase = p.out_off[r];
+                have = false;
             }
-            have = true;
-        } else {
-            uint8_t cin = s_lut[fetch(b + k - 1)];
-            if (HASHED) {
-                uint8_t cout = s_lut[fetch(b - 1)];
-                uint64_t fi = cin < 4 ? s_seed[0][cin] : 0ull, fo = cout < 4 ? s_seed[1][cout] : 0ull;
-                uint64_t ri = cin < 4 ? s_seed[2][cin] : 0ull, ro = cout < 4 ? s_seed[3][cout] : 0ull;
-                fw = rol64d(fw, 1) ^ fo ^ fi;
-                rv = ror64d(rv, 1) ^ ro ^ ri;
+            const size_t L = re - rs;
+            if (L < (size_t)k || (!p.circular && b + k > re)) {
+                have = false;
             } else {
-                if (cin == 255) illegal = true;
-                uint64_t v = (cin >= 4 ? (uint64_t)(cin - 4) : (uint64_t)cin) & 3u;
-                fw = ((fw << 2) | v) & kmask;
-                rv = (rv >> 2) | ((v ^ 3u) << (2 * (k - 1)));
+                if (!have) {
+                    fw = 0;
+                    rv = 0;
+                    if (HASHED) {
+                        for (int i = 0; i < k; ++i) {
+                            uint8_t c = s_lut[fetch(b + i)];
+                            uint64_t sf = c < 4 ? s_seed[0][c] : 0ull;
+                            uint64_t sr = c < 4 ? s_seed[0][3 - c] : 0ull;
+                            fw ^= rol64d(sf, (unsigned)(k - 1 - i));
+                            rv ^= rol64d(sr, (unsigned)i);
+                        }
+                    } else {
+                        for (int i = 0; i < k; ++i) {
+                            uint8_t c = s_lut[fetch(b + i)];
+                            if (c == 255) illegal = true;
+                            uint64_t v = (c >= 4 ? (uint64_t)(c - 4) : (uint64_t)c) & 3u;
+                            fw = ((fw << 2) | v) & kmask;
+                            rv = (rv >> 2) | ((v ^ 3u) << (2 * (k - 1)));
+                        }
+                    }
+                    have = true;
+                } else {
+                    uint8_t cin = s_lut[fetch(b + k - 1)];
+                    if (HASHED) {
+                        uint8_t cout = s_lut[fetch(b - 1)];
+                        uint64_t fi = cin < 4 ? s_seed[0][cin] : 0ull, fo = cout < 4 ? s_seed[1][cout] : 0ull;
+                        uint64_t ri = cin < 4 ? s_seed[2][cin] : 0ull, ro = cout < 4 ? s_seed[3][cout] : 0ull;
+                        fw = rol64d(fw, 1) ^ fo ^ fi;
+                        rv = ror64d(rv, 1) ^ ro ^ ri;
+                    } else {
+                        if (cin == 255) illegal = true;
+                        uint64_t v = (cin >= 4 ? (uint64_t)(cin - 4) : (uint64_t)cin) & 3u;
+                        fw = ((fw << 2) | v) & kmask;
+                        rv = (rv >> 2) | ((v ^ 3u) << (2 * (k - 1)));
+                    }
+                }
+                code = (p.canonical && rv < fw) ? rv : fw;
+                emit = true;
+                if (!FILTER) p.out[obase + (b - rs)] = code;
             }
         }
-        p.out[obase + (b - rs)] = (p.canonical && rv < fw) ? rv : fw;
+        if (FILTER) {
+            const bool keep = emit && code >= p.range_lo && code <= p.range_hi;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) stage[staged + (unsigned)__popc(m & lanemask_lt())] = code;
+            staged += (unsigned)__popc(m);
+            __syncwarp();
+            if (staged >= KM_STAGE - 32) {  // room for one more vote is gone: flush everything
+                flush(staged);
+                staged = 0;
+            }
+        }
     }
+    if (FILTER && staged) flush(staged);
     if (illegal) atomicExch(p.err, (int)UKM_E_ILLEGAL_BASE);
 }
 
@@ -187,9 +237,16 @@ struct LeGen {
     }
 };
 
-// generate every k-mer code / hash of every record into a fresh device buffer
-int generate(ukm_ctx* ctx, ukm_tmp& tmp, const uint8_t* bases, const uint64_t* rec_off, size_t n_rec, int k, unsigned flags,
-             uint64_t max_hash, int where, uint64_t** d_codes, size_t* n_codes, const char* what) {
+// sequences staged on the device + the per-record output offsets
+struct Prepared {
+    KmerArgs a;
+    unsigned long long total = 0;  // k-mers of all records
+    size_t n_bases = 0;
+    bool hashed = false;
+};
+
+int prepare(ukm_ctx* ctx, ukm_tmp& tmp, const uint8_t* bases, const uint64_t* rec_off, size_t n_rec, int k, unsigned flags, int where,
+            Prepared* P, const char* what) {
     const bool hashed = (flags & UKM_F_HASHED) != 0;
     if (!rec_off) return ukm_fail(ctx, UKM_E_ARG, "%s: rec_off == NULL", what);
     if (k < 1 || (!hashed && k > 32) || k > 64) return ukm_fail(ctx, UKM_E_ARG, "%s: k=%d out of range", what, k);
@@ -209,18 +266,17 @@ int generate(ukm_ctx* ctx, ukm_tmp& tmp, const uint8_t* bases, const uint64_t* r
         if (L >= (unsigned long long)k) total += (flags & UKM_F_CIRCULAR) ? L : L - k + 1;  // count.go:324-328: short records skipped
     }
     h_out[n_rec] = total;
-    const size_t n_bases = n_rec ? (size_t)h_rec[n_rec] : 0;
-    *n_codes = (size_t)total;
-    *d_codes = nullptr;
+    P->total = total;
+    P->n_bases = n_rec ? (size_t)h_rec[n_rec] : 0;
+    P->hashed = hashed;
     if (total == 0) return UKM_OK;
     if (n_rec && h_rec[0] != 0) return ukm_fail(ctx, UKM_E_ARG, "%s: rec_off[0] must be 0", what);
     if (!bases) return ukm_fail(ctx, UKM_E_ARG, "%s: bases == NULL", what);
-
     const uint8_t* d_bases = bases;
     if (where != UKM_DEVICE) {
         uint8_t* t;
-        UKM_TRY(tmp.alloc(&t, n_bases + 16));
-        UKM_CUDA(ctx, cudaMemcpyAsync(t, bases, n_bases, cudaMemcpyHostToDevice, ctx->stream));
+        UKM_TRY(tmp.alloc(&t, P->n_bases + 16));
+        UKM_CUDA(ctx, cudaMemcpyAsync(t, bases, P->n_bases, cudaMemcpyHostToDevice, ctx->stream));
         d_bases = t;
     }
     unsigned long long *d_rec, *d_out;
@@ -228,40 +284,66 @@ int generate(ukm_ctx* ctx, ukm_tmp& tmp, const uint8_t* bases, const uint64_t* r
     UKM_TRY(tmp.alloc(&d_out, n_rec + 1));
     UKM_CUDA(ctx, cudaMemcpyAsync(d_rec, h_rec.data(), (n_rec + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     UKM_CUDA(ctx, cudaMemcpyAsync(d_out, h_out.data(), (n_rec + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    UKM_TRY(tmp.alloc(d_codes, (size_t)total + 2));
-
-    KmerArgs a;
+    // pageable host sources (and the local vectors) must stay valid until the copies ran
+    UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KmerArgs& a = P->a;
+    memset(&a, 0, sizeof a);
     a.bases = d_bases;
-    a.n_bases = n_bases;
+    a.n_bases = P->n_bases;
     a.rec_off = d_rec;
     a.out_off = d_out;
     a.n_rec = n_rec;
     a.k = k;
     a.canonical = (flags & UKM_F_CANONICAL) ? 1 : 0;
     a.circular = (flags & UKM_F_CIRCULAR) ? 1 : 0;
-    a.out = *d_codes;
     a.err = ctx->d_err;
-    const int grid = (int)((n_bases + KM_TILE - 1) / KM_TILE);
+    return UKM_OK;
+}
+
+// every code of every record, record-then-position order (the iterators themselves)
+int generate_ordered(ukm_ctx* ctx, Prepared& P, uint64_t* d_codes) {
+    KmerArgs a = P.a;
+    a.out = d_codes;
+    const int grid = (int)((P.n_bases + KM_TILE - 1) / KM_TILE);
+    ukm_stat_scope st(ctx, P.hashed ? "kmer_nthash" : "kmer_encode", (double)P.n_bases + 8.0 * (double)P.total);
+    if (P.hashed) kmer_kernel<true, false><<<grid, KM_THREADS, 0, ctx->stream>>>(a);
+    else kmer_kernel<false, false><<<grid, KM_THREADS, 0, ctx->stream>>>(a);
+    UKM_LAUNCHED(ctx);
+    return UKM_OK;
+}
+
+// codes inside [lo, hi] only, arbitrary order; *n_kept may exceed cap (then the caller retries with narrower ranges)
+int generate_range(ukm_ctx* ctx, Prepared& P, uint64_t lo, uint64_t hi, uint64_t* d_codes, size_t cap, unsigned long long* d_cursor,
+                   size_t* n_kept) {
+    KmerArgs a = P.a;
+    a.out = d_codes;
+    a.range_lo = lo;
+    a.range_hi = hi;
+    a.cursor = d_cursor;
+    a.cap = cap;
+    UKM_CUDA(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
+    const int grid = (int)((P.n_bases + KM_TILE - 1) / KM_TILE);
     {
-        ukm_stat_scope st(ctx, hashed ? "kmer_nthash" : "kmer_encode", (double)n_bases + 8.0 * (double)total);
-        if (hashed) kmer_kernel<true><<<grid, KM_THREADS, 0, ctx->stream>>>(a);
-        else kmer_kernel<false><<<grid, KM_THREADS, 0, ctx->stream>>>(a);
+        ukm_stat_scope st(ctx, P.hashed ? "kmer_nthash_range" : "kmer_encode_range", (double)P.n_bases);
+        if (P.hashed) kmer_kernel<true, true><<<grid, KM_THREADS, 0, ctx->stream>>>(a);
+        else kmer_kernel<false, true><<<grid, KM_THREADS, 0, ctx->stream>>>(a);
         UKM_LAUNCHED(ctx);
     }
-    // pageable host sources must stay valid until the copies above ran
+    UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_cursor, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-
-    if (flags & UKM_F_SCALED) {  // count.go:373: `if scaled && code > maxHash { continue }`
-        uint64_t* d_kept;
-        UKM_TRY(tmp.alloc(&d_kept, (size_t)total + 2));
-        size_t kept = 0;
-        LeGen g{*d_codes, max_hash};
-        UKM_TRY(ukm_dev_select(ctx, g, (size_t)total, d_kept, &kept, "scaled_filter", 8.0 * (double)total));
-        tmp.free_now(*d_codes);
-        *d_codes = d_kept;
-        *n_codes = kept;
-    }
+    *n_kept = (size_t)ctx->h_scratch[0];
+    if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes += 8.0 * (double)std::min(*n_kept, cap);
     return UKM_OK;
+}
+
+// k-mers per key-range pass of `count` (UKM_COUNT_PASS overrides: tests force several passes on small inputs)
+size_t count_pass_limit() {
+    const char* e = getenv("UKM_COUNT_PASS");
+    if (e) {
+        long long v = atoll(e);
+        if (v > 0) return (size_t)v;
+    }
+    return (size_t)2500000000ull;  // 20 GB of codes + 20 GB radix ping-pong per pass
 }
 
 }  // namespace
@@ -272,30 +354,91 @@ extern "C" int ukm_kmers_seq(ukm_ctx* ctx, const uint8_t* bases, const uint64_t*
     if (!out) return ukm_fail(ctx, UKM_E_ARG, "ukm_kmers_seq: out == NULL");
     UKM_CUDA(ctx, cudaSetDevice(ctx->device));
     ukm_tmp tmp(ctx);
+    Prepared P;
+    UKM_TRY(prepare(ctx, tmp, bases, rec_off, n_rec, k, flags, where, &P, "ukm_kmers_seq"));
+    if (P.total == 0) return ukm_deliver(ctx, nullptr, nullptr, 0, out);
     uint64_t* d_codes = nullptr;
-    size_t n = 0;
-    UKM_TRY(generate(ctx, tmp, bases, rec_off, n_rec, k, flags, max_hash, where, &d_codes, &n, "ukm_kmers_seq"));
+    UKM_TRY(tmp.alloc(&d_codes, (size_t)P.total + 2));
+    UKM_TRY(generate_ordered(ctx, P, d_codes));
+    size_t n = (size_t)P.total;
+    if (flags & UKM_F_SCALED) {  // count.go:373: `if scaled && code > maxHash { continue }`
+        uint64_t* d_kept;
+        UKM_TRY(tmp.alloc(&d_kept, n + 2));
+        size_t kept = 0;
+        LeGen g{d_codes, max_hash};
+        UKM_TRY(ukm_dev_select(ctx, g, n, d_kept, &kept, "scaled_filter", 8.0 * (double)n));
+        d_codes = d_kept;
+        n = kept;
+    }
     UKM_TRY(ukm_check_dev_error(ctx, "ukm_kmers_seq"));
     return ukm_deliver(ctx, d_codes, nullptr, n, out);
 }
 
+// count = distinct codes, ascending.  The code space is cut into P equal key ranges; each pass regenerates the
+// codes of its range (the scaled filter `code <= max_hash` is just a tighter upper bound), sorts them
+// (count.go:581) and drops duplicates (the map of count.go:434-436); the passes' results concatenate into the
+// globally sorted answer.  P = 1 unless the k-mers would not fit (config C4: 10^10 k-mers = 80 GB of codes).
 extern "C" int ukm_count_seq(ukm_ctx* ctx, const uint8_t* bases, const uint64_t* rec_off, size_t n_rec, int k, unsigned flags,
                              uint64_t max_hash, int where, ukm_span* out) {
     if (!ctx) return UKM_E_ARG;
     if (!out) return ukm_fail(ctx, UKM_E_ARG, "ukm_count_seq: out == NULL");
     UKM_CUDA(ctx, cudaSetDevice(ctx->device));
     ukm_tmp tmp(ctx);
-    uint64_t* d_codes = nullptr;
-    size_t n = 0;
-    UKM_TRY(generate(ctx, tmp, bases, rec_off, n_rec, k, flags, max_hash, where, &d_codes, &n, "ukm_count_seq"));
-    UKM_TRY(ukm_check_dev_error(ctx, "ukm_count_seq"));
-    if (n == 0) return ukm_deliver(ctx, nullptr, nullptr, 0, out);
+    Prepared P;
+    UKM_TRY(prepare(ctx, tmp, bases, rec_off, n_rec, k, flags, where, &P, "ukm_count_seq"));
+    if (P.total == 0) return ukm_deliver(ctx, nullptr, nullptr, 0, out);
     const int key_bits = (flags & UKM_F_HASHED) ? 64 : 2 * k;
-    UKM_TRY(ukm_dev_sort(ctx, d_codes, nullptr, n, key_bits));  // count.go:581
-    uint64_t* d_uniq = nullptr;
-    UKM_TRY(tmp.alloc(&d_uniq, n + 2));
-    size_t m = 0;
-    UKM_TRY(ukm_dev_fold(ctx, UKM_FOLD_UNIQUE, d_codes, nullptr, n, false, d_uniq, nullptr, &m));  // the map of count.go:434-436
-    UKM_TRY(ukm_check_dev_error(ctx, "ukm_count_seq"));
-    return ukm_deliver(ctx, d_uniq, nullptr, m, out);
+    const uint64_t space_max = key_bits == 64 ? ~0ull : ((1ull << key_bits) - 1);
+    const uint64_t top = (flags & UKM_F_SCALED) ? std::min(max_hash, space_max) : space_max;  // largest code kept
+    // expected codes kept ~ total * (top+1)/2^bits for hashes; for 2-bit codes the estimate is only a start
+    const double frac = (flags & UKM_F_HASHED) ? ((double)top + 1.0) / 18446744073709551616.0 : 1.0;
+    const size_t limit = count_pass_limit();
+    size_t passes = (size_t)(((double)P.total * frac + (double)limit - 1) / (double)limit);
+    if (passes < 1) passes = 1;
+    unsigned long long* d_cursor = nullptr;
+    UKM_TRY(tmp.alloc(&d_cursor, 2));
+    const bool out_dev = out->where == UKM_DEVICE;
+    cudaMemcpyKind kind = out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (int attempt = 0; attempt < 8; ++attempt, passes *= 2) {
+        // per-pass buffers: generous for uniform hashes, retried with twice the passes when a range overflows
+        size_t cap = (size_t)((double)P.total * frac / (double)passes * 1.25) + (1u << 20);
+        if (cap > P.total) cap = (size_t)P.total;
+        uint64_t *d_codes = nullptr, *d_uniq = nullptr;
+        UKM_TRY(tmp.alloc(&d_codes, cap + 2));
+        UKM_TRY(tmp.alloc(&d_uniq, cap + 2));
+        size_t written = 0;
+        bool overflow = false;
+        for (size_t ps = 0; ps < passes && !overflow; ++ps) {
+            // range ps of `passes` over [0, top]
+            const long double width = ((long double)top + 1.0L) / (long double)passes;
+            const uint64_t lo = ps == 0 ? 0 : (uint64_t)(width * (long double)ps);
+            const uint64_t hi = ps + 1 == passes ? top : (uint64_t)(width * (long double)(ps + 1)) - 1;
+            size_t kept = 0;
+            UKM_TRY(generate_range(ctx, P, lo, hi, d_codes, cap, d_cursor, &kept));
+            UKM_TRY(ukm_check_dev_error(ctx, "ukm_count_seq"));
+            if (kept > cap) {
+                overflow = true;
+                break;
+            }
+            if (kept == 0) continue;
+            UKM_TRY(ukm_dev_sort(ctx, d_codes, nullptr, kept, key_bits));
+            size_t m = 0;
+            UKM_TRY(ukm_dev_fold(ctx, UKM_FOLD_UNIQUE, d_codes, nullptr, kept, false, d_uniq, nullptr, &m));
+            if (written + m > out->cap) {
+                out->n = written + m;
+                return ukm_fail(ctx, UKM_E_CAPACITY, "ukm_count_seq: output needs more than %zu elements", out->cap);
+            }
+            if (m) UKM_CUDA(ctx, cudaMemcpyAsync(out->keys + written, d_uniq, m * sizeof(uint64_t), kind, ctx->stream));
+            UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            written += m;
+        }
+        tmp.free_now(d_codes);
+        tmp.free_now(d_uniq);
+        if (!overflow) {
+            UKM_TRY(ukm_check_dev_error(ctx, "ukm_count_seq"));
+            out->n = written;
+            return UKM_OK;
+        }
+    }
+    return ukm_fail(ctx, UKM_E_INTERNAL, "ukm_count_seq: key ranges too skewed for the pass buffers");
 }
