@@ -151,13 +151,14 @@ __device__ __forceinline__ void slice_issue_bulk(T* s, const T* g, long long sta
 
 struct SetopArgs {
     const uint64_t* A;
-    const uint32_t* tA;
+    const uint32_t* tA;  // per-code taxids, or NULL: every code carries gA (unik global taxid)
     const uint32_t* cA;
     long long nA;
     const uint64_t* B;
     const uint32_t* tB;
     const uint32_t* cB;
     long long nB;
+    uint32_t gA, gB;
     const long long* part;
     uint64_t* outK;
     uint32_t* outT;
@@ -204,8 +205,8 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
     const int offB = ((hA + na + 1) & ~1) + slice_offset(p.B, b_lo);
     int hAt = 0, offBt = 0, hAc = 0, offBc = 0;
     if (TAX) {
-        hAt = slice_offset(p.tA, a_lo);
-        offBt = ((hAt + na + 3) & ~3) + slice_offset(p.tB, b_lo);
+        hAt = p.tA ? slice_offset(p.tA, a_lo) : 0;
+        offBt = ((hAt + na + 3) & ~3) + (p.tB ? slice_offset(p.tB, b_lo) : 0);
     }
     if (CNT) {
         hAc = p.cA ? slice_offset(p.cA, a_lo) : 0;
@@ -213,7 +214,10 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
     }
     if (tid == 0) {
         unsigned bytes = slice_body_bytes(p.A, a_lo, na) + slice_body_bytes(p.B, b_lo, nb);
-        if (TAX) bytes += slice_body_bytes(p.tA, a_lo, na) + slice_body_bytes(p.tB, b_lo, nb);
+        if (TAX) {
+            if (p.tA) bytes += slice_body_bytes(p.tA, a_lo, na);
+            if (p.tB) bytes += slice_body_bytes(p.tB, b_lo, nb);
+        }
         if (CNT) {
             if (p.cA) bytes += slice_body_bytes(p.cA, a_lo, na);
             if (p.cB) bytes += slice_body_bytes(p.cB, b_lo, nb);
@@ -222,8 +226,8 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
         slice_issue(s_k, p.A, a_lo, na, &s_bar);
         slice_issue(s_k + offB - slice_offset(p.B, b_lo), p.B, b_lo, nb, &s_bar);
         if (TAX) {
-            slice_issue(s_t, p.tA, a_lo, na, &s_bar);
-            slice_issue(s_t + offBt - slice_offset(p.tB, b_lo), p.tB, b_lo, nb, &s_bar);
+            if (p.tA) slice_issue(s_t, p.tA, a_lo, na, &s_bar);
+            if (p.tB) slice_issue(s_t + offBt - slice_offset(p.tB, b_lo), p.tB, b_lo, nb, &s_bar);
         }
         if (CNT) {
             if (p.cA) slice_issue(s_c, p.cA, a_lo, na, &s_bar);
@@ -259,6 +263,8 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
     int ai = s_part[tid] >> 16, bi = s_part[tid] & 0xffff;
     const int a1 = s_part[tid + 1] >> 16, b1 = s_part[tid + 1] & 0xffff;
 
+#define TXA(i) (p.tA ? sTA[i] : p.gA)
+#define TXB(i) (p.tB ? sTB[i] : p.gB)
     // the reference's three-way compare walk (inter.go:228-257, diff.go:395-431), VT+1 steps
     uint64_t outk[SO_VT + 1];
     uint32_t outt[TAX ? SO_VT + 1 : 1];
@@ -282,24 +288,24 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
         if (OP == OP_INTER) {
             emit = eq;
             if (TAX && eq) {
-                uint32_t qa = sTA[ai], qb = sTB[bi];
+                uint32_t qa = TXA(ai), qb = TXB(bi);
                 if (p.flags & UKM_F_MIX_TAXID) tx = qa == 0 ? qb : (qb == 0 ? qa : lca_dev(p.tax, qa, qb));
                 else tx = lca_dev(p.tax, qa, qb);
             }
         } else if (OP == OP_DIFF) {
             emit = takeA && !eq;
             if (TAX && takeA) {
-                tx = sTA[ai];
+                tx = TXA(ai);
                 if (eq && (p.flags & UKM_F_COMPARE_TAXID)) {
-                    uint32_t qb = sTB[bi];  // keep: same taxid, or subject taxid below the query's
+                    uint32_t qb = TXB(bi);  // keep: same taxid, or subject taxid below the query's
                     if (tx == qb || lca_dev(p.tax, qb, tx) == tx) emit = true;
                 }
             }
         } else if (OP == OP_UNION) {
             emit = takeA || takeB;
             if (TAX && emit) {
-                if (eq) tx = lca_dev(p.tax, sTA[ai], sTB[bi]);
-                else tx = takeA ? sTA[ai] : sTB[bi];
+                if (eq) tx = lca_dev(p.tax, TXA(ai), TXB(bi));
+                else tx = takeA ? TXA(ai) : TXB(bi);
             }
             if (CNT && emit) {
                 uint32_t ca = takeA ? (p.cA ? sCA[ai] : 1u) : 0u;
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
             }
         } else {  // OP_MERGE: keep everything, A first on ties
             emit = takeA || takeB;
-            if (TAX && emit) tx = takeA ? sTA[ai] : sTB[bi];
+            if (TAX && emit) tx = takeA ? TXA(ai) : TXB(bi);
         }
         outk[it] = k;
         if (TAX) outt[it] = tx;
@@ -330,6 +336,8 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
             kb = nk;
         }
     }
+#undef TXA
+#undef TXB
     if (bad) atomicExch(p.err, (int)UKM_E_NOT_SORTED_UNIQUE);
 
     // compact through shared memory (the input slices are dead after the barrier inside the scan)
@@ -753,17 +761,17 @@ __global__ void __launch_bounds__(SS_THREADS) setop_search_kernel(const SetopArg
         bool found = valid && pos[j] < bhi && p.B[pos[j]] == a[j];
         bool emit = valid && (OP == OP_INTER ? found : !found);
         if (TAX && valid) {
-            uint32_t qa = p.tA[base + j];
+            uint32_t qa = p.tA ? p.tA[base + j] : p.gA;
             if (OP == OP_INTER) {
                 if (found) {
-                    uint32_t qb = p.tB[pos[j]];
+                    uint32_t qb = p.tB ? p.tB[pos[j]] : p.gB;
                     if (p.flags & UKM_F_MIX_TAXID) tx[j] = qa == 0 ? qb : (qb == 0 ? qa : lca_dev(p.tax, qa, qb));
                     else tx[j] = lca_dev(p.tax, qa, qb);
                 }
             } else {
                 tx[j] = qa;
                 if (found && (p.flags & UKM_F_COMPARE_TAXID)) {
-                    uint32_t qb = p.tB[pos[j]];
+                    uint32_t qb = p.tB ? p.tB[pos[j]] : p.gB;
                     if (qa == qb || lca_dev(p.tax, qb, qa) == qa) emit = true;
                 }
             }
@@ -793,9 +801,10 @@ __global__ void __launch_bounds__(SS_THREADS) setop_search_kernel(const SetopArg
 // ---- host side: one two-way pass ----------------------------------------------------------
 struct DevSet {
     uint64_t* k = nullptr;
-    uint32_t* t = nullptr;
+    uint32_t* t = nullptr;  // NULL with taxids on: every code carries g
     uint32_t* c = nullptr;
     size_t n = 0;
+    uint32_t g = 0;
 };
 
 constexpr size_t setop_smem(bool tax, bool cnt) {
@@ -947,8 +956,8 @@ int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, boo
     UKM_CUDA(ctx, cudaMemsetAsync(d_status, 0, ((size_t)num_tiles + 4) * sizeof(uint64_t), ctx->stream));
 
     SetopArgs a;
-    a.A = A.k; a.tA = A.t; a.cA = A.c; a.nA = nA;
-    a.B = B.k; a.tB = B.t; a.cB = B.c; a.nB = nB;
+    a.A = A.k; a.tA = A.t; a.cA = A.c; a.nA = nA; a.gA = A.g;
+    a.B = B.k; a.tB = B.t; a.cB = B.c; a.nB = nB; a.gB = B.g;
     a.part = d_part;
     a.outK = out->k; a.outT = out->t; a.outC = out->c;
     a.status = d_status; a.tile_counter = d_counter; a.total_out = d_total;
@@ -1024,12 +1033,14 @@ void free_set(ukm_tmp& tmp, DevSet* s) {
 int stage_set(ukm_ctx* ctx, ukm_tmp& tmp, const ukm_span* in, bool tax, DevSet* s, bool* owned, bool validate = false) {
     ukm_dspan d;
     size_t before = tmp.ptrs.size();
-    UKM_TRY(ukm_stage_in(ctx, tmp, in, tax, &d));
+    // a span without per-code taxids carries its global taxid as a scalar (never materialised)
+    UKM_TRY(ukm_stage_in(ctx, tmp, in, tax && in->taxids != nullptr, &d));
     *owned = tmp.ptrs.size() != before;  // something was allocated for this span
     s->k = d.keys;
     s->t = d.taxids;
     s->c = nullptr;
     s->n = d.n;
+    s->g = in->global_taxid;
     if (validate && d.n > 1) UKM_TRY(ukm_dev_check_sorted_unique(ctx, d.keys, d.n));
     return UKM_OK;
 }
@@ -1042,6 +1053,14 @@ void unstage_set(ukm_tmp& tmp, const ukm_span* in, DevSet* s) {
         tmp.free_now(s->t);
     }
     *s = DevSet();
+}
+
+// a set that still carries its taxid as a scalar gets a real per-code array (only needed when it is
+// handed back unchanged or fed to a kernel without the scalar path)
+int materialize_tax(ukm_ctx* ctx, ukm_tmp& tmp, DevSet* s) {
+    if (s->t) return UKM_OK;
+    UKM_TRY(tmp.alloc(&s->t, s->n + 4));
+    return ukm_dev_fill_u32(ctx, s->t, s->g, s->n);
 }
 
 int check_args(ukm_ctx* ctx, const ukm_span* in, int n_in, ukm_span* out, const char* what) {
@@ -1085,7 +1104,8 @@ int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags
             DevSet S;
             UKM_TRY(alloc_set(tmp, &S, F.n, tax, false));
             UKM_CUDA(ctx, cudaMemcpyAsync(S.k, F.k, F.n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-            if (tax) UKM_CUDA(ctx, cudaMemcpyAsync(S.t, F.t, F.n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (tax && F.t) UKM_CUDA(ctx, cudaMemcpyAsync(S.t, F.t, F.n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            else if (tax) UKM_TRY(ukm_dev_fill_u32(ctx, S.t, F.g, F.n));
             unstage_set(tmp, &in[i], &F);
             UKM_TRY(ukm_dev_sort(ctx, S.k, tax ? S.t : nullptr, S.n = in[i].n, 64));
             DevSet U;
@@ -1116,6 +1136,7 @@ int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags
         which ^= 1;
     }
     UKM_TRY(ukm_check_dev_error(ctx, what));
+    if (tax) UKM_TRY(materialize_tax(ctx, tmp, &cur));
     return ukm_deliver(ctx, cur.k, tax ? cur.t : nullptr, cur.n, out);
 }
 
@@ -1169,6 +1190,7 @@ int run_tree(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags,
     }
     UKM_TRY(ukm_check_dev_error(ctx, what));
     DevSet r = level[0];
+    if (tax) UKM_TRY(materialize_tax(ctx, tmp, &r));
     if (fold_mode != UKM_FOLD_PLAIN) {
         DevSet f;
         UKM_TRY(alloc_set(tmp, &f, r.n + 2, tax, false));

@@ -58,32 +58,47 @@ class KeyRangeExchange:
             counts = c.cpu()
         return offsets, counts
 
-    def exchange(self, local_files: Dict[int, torch.Tensor], n_files: int, splitters: np.ndarray) -> List[torch.Tensor]:
-        """One all-to-all-v.  Returns, for every file id in order, this rank's key-range slice."""
+    def exchange(self, local_files: Dict[int, torch.Tensor], n_files: int, splitters: np.ndarray,
+                 local_values: Dict[int, torch.Tensor] = None):
+        """One all-to-all-v.  Returns, for every file id in order, this rank's key-range slice of the keys
+        (and, if `local_values` holds a per-key array for every local file -- taxids --, a second list with the
+        matching value slices, moved in the same grouped call)."""
         G, me = self.world, self.rank
         offsets, counts = self.plan(local_files, n_files, splitters)
+        with_vals = local_values is not None
         out: List[torch.Tensor] = [None] * n_files  # type: ignore
+        outv: List[torch.Tensor] = [None] * n_files  # type: ignore
+        ref = next(iter(local_files.values())) if local_files else None
+        refv = next(iter(local_values.values())) if (with_vals and local_values) else None
         ops = []
         for f in range(n_files):
             o = owner_of_file(f, G)
             if o == me:
                 t, off = local_files[f], offsets[f]
                 out[f] = t[off[me]:off[me + 1]]  # own slice: a view, no copy
+                if with_vals:
+                    outv[f] = local_values[f][off[me]:off[me + 1]]
                 for r in range(G):
                     if r != me and off[r + 1] > off[r]:
                         ops.append(dist.P2POp(dist.isend, t[off[r]:off[r + 1]], r, group=self.group))
+                        if with_vals:
+                            ops.append(dist.P2POp(dist.isend, local_values[f][off[r]:off[r + 1]], r, group=self.group))
             else:
                 n = int(counts[f, me])
-                ref = next(iter(local_files.values())) if local_files else None
                 buf = torch.empty(n, dtype=ref.dtype if ref is not None else torch.int64,
                                   device=ref.device if ref is not None else "cpu")
                 out[f] = buf
+                if with_vals:
+                    outv[f] = torch.empty(n, dtype=refv.dtype if refv is not None else torch.int32,
+                                          device=buf.device)
                 if n:
                     ops.append(dist.P2POp(dist.irecv, buf, o, group=self.group))
+                    if with_vals:
+                        ops.append(dist.P2POp(dist.irecv, outv[f], o, group=self.group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        return out
+        return (out, outv) if with_vals else out
 
     @staticmethod
     def exchanged_bytes(counts: torch.Tensor, world: int) -> int:
