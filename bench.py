@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--detail", action="store_true", help="print a per-kernel table to stderr")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N>1: NVLink peer pulls (copy engines, overlapped) or one NCCL all-to-all-v")
     args = ap.parse_args()
     args.universe, args.ref_universe, args.cpu_universe = int(args.universe), int(args.ref_universe), int(args.cpu_universe)
     if args.impl == "reference":
@@ -182,7 +182,7 @@ def main():
     import torch.distributed as dist
 
     from unikmer_b200 import Engine
-    from unikmer_b200.dist import KeyRangeExchange, equal_width_splitters, owner_of_file
+    from unikmer_b200.dist import KeyRangeExchange, PeerPullExchange, equal_width_splitters, owner_of_file
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,16 +216,38 @@ def main():
         total_in = int(sizes.sum().item())
         splitters = equal_width_splitters(world, 62)
         ex = KeyRangeExchange(eng, rank, world)
+        pex = None
+        if world > 1 and args.exchange == "peer":
+            try:
+                pex = PeerPullExchange(eng, rank, world, local_files, N_FILES)
+            except Exception as e:  # no peer access / IPC: fall back to the NCCL all-to-all-v
+                if rank == 0:
+                    print(f"peer exchange unavailable ({e}); using NCCL", file=sys.stderr)
+                pex = None
+            ok = torch.tensor([1 if pex is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                pex = None
 
         def step():
-            if world > 1:
-                files = ex.exchange(local_files, N_FILES, splitters)
-            else:
+            if world == 1:
                 files = [local_files[f] for f in range(N_FILES)]
-            i, _ = eng.inter(files)
-            d, _ = eng.diff(files)
-            u, _ = eng.union(files)
-            return i, d, u
+                return eng.inter(files)[0], eng.diff(files)[0], eng.union(files)[0]
+            if pex is None:
+                files = ex.exchange(local_files, N_FILES, splitters)
+                return eng.inter(files)[0], eng.diff(files)[0], eng.union(files)[0]
+            # peer pulls run on the copy engines while the first level of the union tree merges the pairs that
+            # have already arrived; inter / diff / the upper union levels follow (same passes as eng.union(files))
+            files, ev = pex.exchange_async(splitters)
+            lvl = []
+            for q in range(0, N_FILES, 2):
+                pex.wait(ev, (q, q + 1))
+                lvl.append(eng.union(files[q:q + 2])[0])
+            i = eng.inter(files)[0]
+            d = eng.diff(files)[0]
+            while len(lvl) > 1:
+                lvl = [eng.union(lvl[q:q + 2])[0] for q in range(0, len(lvl), 2)]
+            return i, d, lvl[0]
 
         res = None
         for _ in range(args.warmup):
@@ -361,7 +383,9 @@ def main():
             "config": {"workload": f"C3: inter+diff+union over 8 sorted duplicate-free files x ~{U // 2:.1e} k=31 uint64 k-mers "
                                    f"(universe {U:.0e}, {total_in} k-mers in); each op reads all inputs",
                        "inputs": "device-resident, 32 GB >> 126 MB L2 (no L2 flush needed)" if U >= 10**8 else "device-resident",
-                       "parallelism": f"key-range shards x{world}, one NCCL all-to-all-v per step" if world > 1 else "1 GPU",
+                       "parallelism": ("1 GPU" if world == 1 else f"key-range shards x{world}, " +
+                                       ("NVLink peer pulls on the copy engines (CUDA IPC), overlapped with union level 1"
+                                        if pex is not None else "one NCCL all-to-all-v per step")),
                        "kmers_per_step": 3 * total_in},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "check": check,

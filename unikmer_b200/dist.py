@@ -125,3 +125,74 @@ def _uneven_all_gather(bufs: Sequence[torch.Tensor], piece: torch.Tensor, rank: 
         if r == rank:
             bufs[r].copy_(piece)
         dist.broadcast(bufs[r], src=r, group=group)
+
+
+class PeerPullExchange:
+    """Key-range exchange over NVLink peer mappings, driven by the copy engines.
+
+    Set-up (once, like creating a communicator): every rank shares CUDA-IPC handles of its resident files, every
+    other rank maps them.  Per step each rank PULLS its key-range slice of every remote file with an asynchronous
+    peer copy on side streams -- no NCCL kernels, no SMs, so the transfers overlap the merge passes that already
+    have their inputs -- and hands back (tensor, event) pairs; consumers wait on the event of the file they need.
+    """
+
+    def __init__(self, backend, rank: int, world: int, local_files: Dict[int, torch.Tensor], n_files: int, group=None,
+                 n_streams: int = 4):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.backend, self.rank, self.world, self.group, self.n_files = backend, rank, world, group, n_files
+        self.local = local_files
+        self.device = next(iter(local_files.values())).device
+        shared = {f: reduce_tensor(t) for f, t in local_files.items()}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, shared, group=group)
+        self.peer: Dict[int, torch.Tensor] = {}
+        for r, d in enumerate(everyone):
+            if r == rank:
+                continue
+            for f, (fn, args) in d.items():
+                self.peer[f] = fn(*args)  # a tensor on the owner's device, backed by the owner's memory
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+        self.bufs: Dict[int, torch.Tensor] = {}
+
+    def exchange_async(self, splitters: np.ndarray):
+        """Returns (slices, events): slices[f] = this rank's key-range slice of file f; events[f] = CUDA event to wait
+        on before reading it (None for local views)."""
+        G, me, n_files = self.world, self.rank, self.n_files
+        # slice boundaries: the owner binary-searches its files; one small all-reduce shares them
+        bounds = torch.zeros(n_files, G + 1, dtype=torch.int64)
+        for f, t in self.local.items():
+            bounds[f] = torch.from_numpy(np.asarray(self.backend.partition_sorted(t, splitters), dtype=np.int64))
+        b = bounds.to(self.device)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group)
+        bounds = b.cpu()
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        slices: List[torch.Tensor] = [None] * n_files  # type: ignore
+        events: List[torch.cuda.Event] = [None] * n_files  # type: ignore
+        for i, f in enumerate(range(n_files)):
+            lo, hi = int(bounds[f, me]), int(bounds[f, me + 1])
+            if f in self.local:
+                slices[f] = self.local[f][lo:hi]
+                continue
+            n = hi - lo
+            buf = self.bufs.get(f)
+            if buf is None or buf.shape[0] < n:
+                buf = torch.empty(int(n * 1.05) + 16, dtype=self.peer[f].dtype, device=self.device)
+                self.bufs[f] = buf
+            s = self.streams[i % len(self.streams)]
+            s.wait_event(ready)  # do not overwrite a buffer the previous step may still read
+            with torch.cuda.stream(s):
+                buf[:n].copy_(self.peer[f][lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s)
+            slices[f] = buf[:n]
+            events[f] = ev
+        self.bytes_pulled = sum(int(slices[f].shape[0]) * 8 for f in range(n_files) if f not in self.local)
+        return slices, events
+
+    def wait(self, events, files):
+        cur = torch.cuda.current_stream(self.device)
+        for f in files:
+            if events[f] is not None:
+                cur.wait_event(events[f])
