@@ -399,5 +399,21 @@ def main():
     return 0
 
 
+def _quiet_stdout():
+    """Libraries (NCCL's version banner) print to fd 1; the contract is ONE JSON line on stdout.  Point fd 1 at
+    stderr for the run and keep the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 if __name__ == "__main__":
+    _out = _quiet_stdout()
+    _print = print
+
+    def print(*a, **k):  # noqa: A001 -- result lines go to the real stdout
+        k.setdefault("file", _out)
+        _print(*a, **k)
+        _out.flush()
     sys.exit(main())
