@@ -236,18 +236,20 @@ def main():
             if pex is None:
                 files = ex.exchange(local_files, N_FILES, splitters)
                 return eng.inter(files)[0], eng.diff(files)[0], eng.union(files)[0]
-            # peer pulls run on the copy engines while the first level of the union tree merges the pairs that
-            # have already arrived; inter / diff / the upper union levels follow (same passes as eng.union(files))
+            # peer pulls run on the copy engines while the passes whose inputs have arrived run: per arriving pair of
+            # files one union level-1 merge and the next two links of the inter / diff chains (the same passes, in the
+            # same file order, as eng.inter(files) / eng.diff(files) / eng.union(files)); the upper union levels follow
             files, ev = pex.exchange_async(splitters)
-            lvl = []
+            lvl, ci, cd = [], None, None
             for q in range(0, N_FILES, 2):
                 pex.wait(ev, (q, q + 1))
-                lvl.append(eng.union(files[q:q + 2])[0])
-            i = eng.inter(files)[0]
-            d = eng.diff(files)[0]
+                pair = files[q:q + 2]
+                lvl.append(eng.union(pair)[0])
+                ci = eng.inter(pair if ci is None else [ci] + pair)[0] if (ci is None or ci.shape[0]) else ci
+                cd = eng.diff(pair if cd is None else [cd] + pair)[0] if (cd is None or cd.shape[0]) else cd
             while len(lvl) > 1:
                 lvl = [eng.union(lvl[q:q + 2])[0] for q in range(0, len(lvl), 2)]
-            return i, d, lvl[0]
+            return ci, cd, lvl[0]
 
         res = None
         for _ in range(args.warmup):
@@ -384,7 +386,7 @@ def main():
                                    f"(universe {U:.0e}, {total_in} k-mers in); each op reads all inputs",
                        "inputs": "device-resident, 32 GB >> 126 MB L2 (no L2 flush needed)" if U >= 10**8 else "device-resident",
                        "parallelism": ("1 GPU" if world == 1 else f"key-range shards x{world}, " +
-                                       ("NVLink peer pulls on the copy engines (CUDA IPC), overlapped with union level 1"
+                                       ("NVLink peer pulls on the copy engines (CUDA IPC), overlapped with the passes whose inputs have arrived"
                                         if pex is not None else "one NCCL all-to-all-v per step")),
                        "kmers_per_step": 3 * total_in},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
