@@ -195,8 +195,7 @@ def member_files(N, nfiles, S=3, T=4):
 
 @pytest.mark.parametrize("kernel", ["pipe:0", "pipe:1", "pipe:2", "pipe:3", "pipe:4", "pipe:5", "vt:11", "vt:15", "vt:19", "vt:23"])
 @pytest.mark.parametrize("skew", ["0", "3"])
-@pytest.mark.parametrize("dyn", ["1", "0"])
-def test_setop_kernel_variants(eng, kernel, skew, dyn, monkeypatch):
+def test_setop_kernel_variants(eng, kernel, skew, monkeypatch):
     """Every shape of the keys-only kernels (persistent pipeline / one tile per CTA), with and without
     the search path for skewed pairs."""
     kind, cfg = kernel.split(":")
@@ -204,9 +203,6 @@ def test_setop_kernel_variants(eng, kernel, skew, dyn, monkeypatch):
     if kind == "vt":
         monkeypatch.setenv("UKM_SETOP_VT", cfg)
     monkeypatch.setenv("UKM_SETOP_SKEW", skew)
-    monkeypatch.setenv("UKM_SETOP_DYN", dyn)
-    if kind == "vt" and dyn == "0":
-        pytest.skip("UKM_SETOP_DYN only affects the pipeline kernels")
     for N, nf in ((400_000, 8), (3_000_000, 3), (5_000, 2)):
         files = member_files(N, nf)
         same(eng.inter(files)[0], oracle.inter(files)[0], f"inter {N}")

@@ -6,8 +6,8 @@ eng = Engine(0); stream = torch.cuda.Stream(); eng.use_stream(stream.cuda_stream
 with torch.cuda.stream(stream):
     U = 10**9
     a = eng.synth_member_file(0, U, U, 3, 4, 0).clone(); b = eng.synth_member_file(0, U, U, 3, 4, 1).clone()
-    for pipe, dyn in (("1", "1"), ("1", "0"), ("0", "1"), ("0", "0")):
-        os.environ["UKM_SETOP_PIPE"] = pipe; os.environ["UKM_SETOP_SKEW"] = "0"; os.environ["UKM_SETOP_DYN"] = dyn
+    for pipe in ("0", "2", "off"):
+        os.environ["UKM_SETOP_PIPE"] = pipe; os.environ["UKM_SETOP_SKEW"] = "0"
         r = {}
         for name, fn in (("merge", lambda: eng.merge([a, b])), ("union", lambda: eng.union([a, b])), ("inter", lambda: eng.inter([a, b])), ("diff", lambda: eng.diff([a, b]))):
             eng.stats_reset(); eng.stats_enable(True)
@@ -15,4 +15,4 @@ with torch.cuda.stream(stream):
             eng.stats_enable(False)
             st = eng.stats()
             r[name] = {k: round(v["ms"] / v["launches"], 3) for k, v in st.items()}
-        print(json.dumps({"pipe": pipe, "dyn": dyn, **r}), flush=True)
+        print(json.dumps({"pipe": pipe, **r}), flush=True)

@@ -691,198 +691,6 @@ __global__ void __launch_bounds__(NT + PIPE_AUX, MINB) setop_pipe_kernel(const S
     }
 }
 
-// Dynamic variant: tiles are handed out by an atomic counter instead of round-robin, so a CTA that runs slower
-// (far-die L2, an unlucky SM partner) simply takes fewer tiles instead of pacing the whole grid; offsets come
-// from a 256-wide decoupled look-back done by the prefix warp, still DEFER tiles ahead of the copy-out.
-template <int OP, int NT, int VT, int SLOTS, int MINB>
-__global__ void __launch_bounds__(NT + PIPE_AUX, MINB) setop_pipe_dyn_kernel(const SetopArgs p) {
-    constexpr int T = NT * VT;
-    constexpr int SLOT = T + 8;
-    constexpr int NW = NT / 32;
-    constexpr int DEFER = SLOTS - 2;  // copy-out lag in tiles
-    extern __shared__ __align__(16) unsigned char so_smem[];
-    uint64_t* s_slots = reinterpret_cast<uint64_t*>(so_smem);  // SLOTS * SLOT
-    __shared__ __align__(8) uint64_t full_bar[SLOTS], empty_bar[SLOTS], pre_bar[SLOTS];
-    __shared__ unsigned long long s_cnt[SLOTS], s_pre[SLOTS];
-    __shared__ PipeGeom s_geom[SLOTS];
-    __shared__ int s_tileid[SLOTS];  // tile taken for the slot, -1 = no more tiles
-    __shared__ __align__(8) uint64_t cnt_bar[SLOTS];
-    __shared__ int s_part[NT + 1];
-    __shared__ unsigned s_scan[NW + 2];
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < SLOTS; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], NT);  // every consumer thread arrives after its share of the copy-out
-            mbar_init(&pre_bar[s], 1);
-            mbar_init(&cnt_bar[s], 1);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-    const unsigned lane = lane_id();
-
-    if (threadIdx.x < 32) {
-        // ================= loader warp =================
-        for (int li = 0;; ++li) {
-            const int s = li % SLOTS, u = li / SLOTS;
-            if (u > 0 && !mbar_wait(&empty_bar[s], (unsigned)(u - 1) & 1u)) {
-                if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
-            }
-            int tile = 0;
-            if (lane == 0) {
-                tile = (int)atomicAdd(p.tile_counter, 1u);
-                if (tile >= p.num_tiles) tile = -1;
-                s_tileid[s] = tile;
-                if (tile < 0) {
-                    mbar_arrive(&full_bar[s]);  // release: the sentinel is visible to the consumers
-                } else {
-                    const long long a_lo = p.part[2 * tile], b_lo = p.part[2 * tile + 1];
-                    const int na = (int)(p.part[2 * tile + 2] - a_lo), nb = (int)(p.part[2 * tile + 3] - b_lo);
-                    const int hA = slice_offset(p.A, a_lo), hB = slice_offset(p.B, b_lo);
-                    const int offB = ((hA + na + 1) & ~1) + hB;
-                    uint64_t* slot = s_slots + (size_t)s * SLOT;
-                    PipeGeom g;
-                    g.base = a_lo + b_lo;
-                    g.na = na; g.nb = nb; g.hA = hA; g.offB = offB;
-                    s_geom[s] = g;
-                    const unsigned bytes = slice_body_bytes(p.A, a_lo, na) + slice_body_bytes(p.B, b_lo, nb);
-                    slice_issue_plain(slot, p.A, a_lo, na);
-                    slice_issue_plain(slot + offB - hB, p.B, b_lo, nb);
-                    mbar_expect_tx(&full_bar[s], bytes);
-                    slice_issue_bulk(slot, p.A, a_lo, na, &full_bar[s]);
-                    slice_issue_bulk(slot + offB - hB, p.B, b_lo, nb, &full_bar[s]);
-                }
-            }
-            tile = __shfl_sync(0xffffffffu, tile, 0);
-            if (tile < 0) break;
-        }
-        return;
-    }
-    if (threadIdx.x < 64) {
-        // ================= prefix warp =================
-        if (OP == OP_MERGE) return;  // positions are data independent
-        for (int bi = 0;; ++bi) {
-            const int s = bi % SLOTS, u = bi / SLOTS;
-            if (!mbar_wait(&cnt_bar[s], (unsigned)u & 1u)) {
-                if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
-                return;
-            }
-            const int tile = s_tileid[s];
-            if (tile < 0) return;
-            const unsigned long long total = s_cnt[s];
-            const unsigned long long prefix = lookback_wide(p.status, tile, total, false, p.err);
-            if (lane == 0) {
-                s_pre[s] = prefix;
-                if (tile == p.num_tiles - 1) *p.total_out = prefix + total;
-                mbar_arrive(&pre_bar[s]);
-            }
-            __syncwarp();
-        }
-    }
-
-    // ================= consumers =================
-    const int tid = (int)threadIdx.x - PIPE_AUX;
-    int n_my = 1 << 30;  // becomes the number of tiles this CTA got once the loader posts the sentinel
-    for (int i = 0; i < n_my + DEFER; ++i) {
-        unsigned emitmask = 0;
-        uint64_t outk[VT + 1];
-        unsigned off = 0;
-        uint64_t* slot = nullptr;
-        if (i < n_my) {
-            const int s = i % SLOTS, u = i / SLOTS;
-            slot = s_slots + (size_t)s * SLOT;
-            if (!mbar_wait(&full_bar[s], (unsigned)u & 1u)) {
-                if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
-            }
-            const int tile = s_tileid[s];
-            if (tile < 0) {  // no more tiles: tell the prefix warp, then only the deferred copy-outs remain
-                n_my = i;
-                if (tid == 0 && OP != OP_MERGE) mbar_arrive(&cnt_bar[s]);
-                slot = nullptr;
-            }
-          if (tile >= 0) {
-            const PipeGeom g = s_geom[s];
-            const int na = g.na, nb = g.nb;
-            const uint64_t* sA = slot + g.hA;
-            const uint64_t* sB = slot + g.offB;
-            const int total = na + nb;
-            {
-                int diag = tid * VT;
-                if (diag > total) diag = total;
-                int a = merge_path(sA, na, sB, nb, diag);
-                int b = diag - a;
-                if (OP != OP_MERGE) {
-                    if (a > 0 && b < nb && sA[a - 1] == sB[b]) ++b;
-                }
-                s_part[tid] = (a << 16) | b;
-                if (tid == 0) s_part[NT] = (na << 16) | nb;
-            }
-            named_bar_sync(1, NT);
-            int ai = s_part[tid] >> 16, bi = s_part[tid] & 0xffff;
-            const int a1 = s_part[tid + 1] >> 16, b1 = s_part[tid + 1] & 0xffff;
-            uint64_t ka = sA[ai], kb = sB[bi];
-#pragma unroll
-            for (int it = 0; it <= VT; ++it) {
-                const bool pa = ai < a1, pb = bi < b1;
-                const bool gt = ka > kb;
-                const bool takeA = pa && (!pb || !gt);
-                const bool takeB = pb && !takeA;
-                const bool eq = takeA && pb && (ka == kb);
-                bool emit;
-                if (OP == OP_INTER) emit = eq;
-                else if (OP == OP_DIFF) emit = takeA && !eq;
-                else emit = takeA || takeB;
-                outk[it] = (OP == OP_INTER || OP == OP_DIFF) ? ka : (takeA ? ka : kb);
-                emitmask |= (emit ? 1u : 0u) << it;
-                if (takeA) ka = sA[++ai];
-                if (takeB || (eq && OP != OP_MERGE)) kb = sB[++bi];
-            }
-            unsigned tile_total;
-            off = group_excl_scan_u32<NT>((unsigned)__popc(emitmask), (unsigned)tid, s_scan, &tile_total, 1);
-            // every consumer is past its walk (two barriers inside the scan): the slot may be overwritten
-            if (tid == 0) {
-                s_cnt[s] = tile_total;
-                if (OP != OP_MERGE) {
-                    if (tile > 0) st_relaxed_u64(&p.status[tile], UKM_LB_PARTIAL | (uint64_t)tile_total);
-                    mbar_arrive(&cnt_bar[s]);  // release: s_cnt visible to the prefix warp
-                }
-            }
-          }
-        }
-        // copy tile i-DEFER out while this tile's count travels
-        if (i >= DEFER && i - DEFER < n_my) {
-            const int ip = i - DEFER;
-            const int sp = ip % SLOTS, up = ip / SLOTS;
-            const uint64_t* prev = s_slots + (size_t)sp * SLOT;
-            unsigned long long prefix;
-            if (OP == OP_MERGE) {
-                prefix = (unsigned long long)s_geom[sp].base;
-                if (tid == 0 && s_tileid[sp] == p.num_tiles - 1) *p.total_out = prefix + s_cnt[sp];
-            } else {
-                if (!mbar_wait(&pre_bar[sp], (unsigned)up & 1u)) {
-                    if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
-                }
-                prefix = s_pre[sp];
-            }
-            const unsigned n_prev = (unsigned)s_cnt[sp];
-            uint64_t* dst = p.outK + prefix;
-            for (unsigned j = tid; j < n_prev; j += NT) dst[j] = prev[j];
-            mbar_arrive(&empty_bar[sp]);  // release: my reads of the slot are done
-        }
-        // stage this tile's outputs in place
-        if (i < n_my && slot) {
-            unsigned o = off;
-#pragma unroll
-            for (int it = 0; it <= VT; ++it) {
-                if (emitmask & (1u << it)) slot[o++] = outk[it];
-            }
-        }
-        named_bar_sync(1, NT);  // staged tile (and s_cnt) visible to every consumer before a later copy-out
-    }
-}
-
-
 // ---- search path for skewed pairs (|B| >> |A|): inter / diff -------------------------------------
 // When the running set A is much smaller than the next file B (inter.go / diff.go after a few files),
 // walking all of B is wasted work: every thread looks its A elements up in B's window for the tile
@@ -1058,19 +866,11 @@ int launch_fast(ukm_ctx* ctx, int op, const SetopArgs& a) {
     }
 }
 
-// UKM_SETOP_DYN=0 selects the round-robin pipeline (per-iteration count all-gather) instead of the dynamic one
-bool pipe_dynamic() {
-    const char* e = getenv("UKM_SETOP_DYN");
-    return !(e && e[0] == '0');
-}
-
 template <int OP, int NT, int VT, int SLOTS, int MINB>
 int launch_pipe_v(ukm_ctx* ctx, SetopArgs a) {
     constexpr size_t smem = (size_t)SLOTS * (NT * VT + 8) * 8;
-    const bool dyn = pipe_dynamic();
-    auto kern = dyn ? setop_pipe_dyn_kernel<OP, NT, VT, SLOTS, MINB> : setop_pipe_kernel<OP, NT, VT, SLOTS, MINB>;
-    static int ctas_per_sm_v[2] = {0, 0};  // per instantiation and variant
-    int& ctas_per_sm = ctas_per_sm_v[dyn ? 1 : 0];
+    auto kern = setop_pipe_kernel<OP, NT, VT, SLOTS, MINB>;
+    static int ctas_per_sm = 0;  // per instantiation
     if (ctas_per_sm == 0) {
         UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
