@@ -255,8 +255,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
 }
 // bounded wait: returns false if the watchdog expired
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity) {
-    for (unsigned spin = 0; spin < UKM_WATCHDOG_SPINS; ++spin)
+    for (unsigned spin = 0; spin < UKM_WATCHDOG_SPINS; ++spin) {
         if (mbar_try_wait(bar, parity)) return true;
+        if (spin >= 2) __nanosleep(128);  // a long wait: stop competing for issue slots with the warps that have work
+    }
     return false;
 }
 // global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16
