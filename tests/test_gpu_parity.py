@@ -570,6 +570,24 @@ def test_large_sort_properties(eng):
     del d
 
 
+def test_c2_full_size_sort(eng):
+    """C2 at BASELINE.json's full size: 1e9 random 62-bit keys (8 GB) sorted on the device, checked through
+    size-independent properties: non-decreasing, key sum preserved (mod 2^64), and every generated key that is below
+    the 2e6-th smallest (taken from the first 5e7 generated keys, via the oracle's generator) sits in the sorted head."""
+    n = 1_000_000_000
+    d = eng.synth_random_keys(0, n, 2)
+    s0 = int(d.sum().item())
+    eng.sort(d, key_bits=62)
+    assert bool((d[1:] >= d[:-1]).all().item()), "not sorted"  # keys < 2^62: signed compare is fine
+    assert int(d.sum().item()) == s0
+    bound = int(d[2_000_000].item())
+    gen = oracle.random_keys(0, 50_000_000, 2)
+    small = gen[gen < np.uint64(bound)]
+    head = d[:2_000_001].cpu().numpy().view(np.uint64)
+    assert len(small) > 50_000 and np.isin(small, head).all()
+    del d
+
+
 def test_large_setop_properties(eng):
     """C3-like at 8 x 2.5e7: inter is a subset of every input, diff is disjoint from the subjects,
     |A u B| = |A| + |B| - |A n B|, expected cardinalities ~ N/256."""

@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""C4 (BASELINE.json configs[3]): `count -k 31 -K -H -s` over a synthetic FASTA of R records x L bases, device-resident.
+
+    python tools/run_c4.py [--records 100 --length 1e8]      # 10 Gbp = the full config (needs ~150 GB of HBM)
+
+Generator: base i of record r = "ACGT"[(sm64(5 + (r<<32) + i/32) >> (2*(i%32))) & 3].
+Checks: output strictly increasing, count <= number of k-mers, and record 0's first 200 kbp counted separately equals the
+CPU oracle bit for bit.  Prints one JSON line."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from unikmer_b200 import Engine  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--records", type=int, default=100)
+    ap.add_argument("--length", type=float, default=1e8)
+    ap.add_argument("--pass-limit", type=float, default=1.5e9)
+    args = ap.parse_args()
+    R, L = args.records, int(args.length)
+    os.environ["UKM_COUNT_PASS"] = str(int(args.pass_limit))
+    eng = Engine(0)
+    stream = torch.cuda.Stream()
+    eng.use_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        bases = torch.empty(R * L, dtype=torch.uint8, device="cuda")
+        for r in range(R):
+            bases[r * L:(r + 1) * L] = eng.synth_bases(r, 0, L, 5)
+        off = torch.arange(0, R + 1, dtype=torch.int64, device="cuda") * L
+        torch.cuda.synchronize()
+        eng.stats_reset()
+        eng.stats_enable(True)
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = eng.count(bases, off, 31, canonical=True, hashed=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        eng.stats_enable(False)
+        st = eng.stats()
+        n_kmers = R * (L - 30)
+        # properties at full size
+        u = out.view(torch.int64)
+        # compare as unsigned: flip the sign bit
+        flipped = u ^ torch.tensor(-2**63, dtype=torch.int64, device="cuda")
+        increasing = bool((flipped[1:] > flipped[:-1]).all().item())
+        import oracle
+        w = 200_000
+        seq = oracle.synth_bases(0, 0, w, 5)
+        exp = oracle.count(seq, np.array([0, w], dtype=np.uint64), 31, canonical=True, hashed=True)
+        got = eng.count(bases[:w].contiguous(), torch.tensor([0, w], dtype=torch.int64, device="cuda"), 31, canonical=True, hashed=True)
+        exact = bool(np.array_equal(got.cpu().numpy().view(np.uint64), exp))
+        # every hash of the window must be present in the full result
+        present = bool(torch.isin(got.view(torch.int64), u).all().item()) if u.shape[0] < 3_000_000_000 else None
+    print(json.dumps({"config": f"C4 count -k 31 -K -H -s, {R} records x {L:.0e} bases", "bases": R * L, "kmers": n_kmers,
+                      "distinct": int(out.shape[0]), "ms": ms, "wall_s": wall, "kmers_per_s": n_kmers / ms * 1e3,
+                      "strictly_increasing": increasing, "window_exact_vs_oracle": exact, "window_subset_of_result": present,
+                      "kernels_ms": {k: round(v["ms"], 1) for k, v in st.items()}}))
+    if not (increasing and exact):
+        raise SystemExit("C4 self-check failed")
+
+
+if __name__ == "__main__":
+    main()
