@@ -76,6 +76,7 @@ struct KmerArgs {
     uint64_t range_lo, range_hi;
     unsigned long long* cursor;  // number of codes appended so far
     unsigned long long cap;      // capacity of out; codes beyond it are counted but not stored
+    unsigned tile_stride;        // process every tile_stride-th tile only (sampling pass); 1 = all
 };
 
 constexpr int KM_STAGE = 256;  // per-warp staging ring of the FILTER mode (flushed 128 codes at a time)
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmer_kernel(const KmerArgs p) {
 
     const int tid = threadIdx.x;
     const unsigned lane = lane_id();
-    const size_t B0 = (size_t)blockIdx.x * KM_TILE;
+    const size_t B0 = (size_t)blockIdx.x * (FILTER ? (size_t)p.tile_stride : (size_t)1) * KM_TILE;
     const size_t tile_end = (B0 + KM_TILE + KM_HALO < p.n_bases) ? B0 + KM_TILE + KM_HALO : p.n_bases;
     const int tile_len = (int)(tile_end - B0);
     build_lut(s_lut);
@@ -297,6 +298,7 @@ int prepare(ukm_ctx* ctx, ukm_tmp& tmp, const uint8_t* bases, const uint64_t* re
     a.canonical = (flags & UKM_F_CANONICAL) ? 1 : 0;
     a.circular = (flags & UKM_F_CIRCULAR) ? 1 : 0;
     a.err = ctx->d_err;
+    a.tile_stride = 1;
     return UKM_OK;
 }
 
@@ -314,15 +316,17 @@ int generate_ordered(ukm_ctx* ctx, Prepared& P, uint64_t* d_codes) {
 
 // codes inside [lo, hi] only, arbitrary order; *n_kept may exceed cap (then the caller retries with narrower ranges)
 int generate_range(ukm_ctx* ctx, Prepared& P, uint64_t lo, uint64_t hi, uint64_t* d_codes, size_t cap, unsigned long long* d_cursor,
-                   size_t* n_kept) {
+                   size_t* n_kept, unsigned tile_stride = 1) {
     KmerArgs a = P.a;
     a.out = d_codes;
     a.range_lo = lo;
     a.range_hi = hi;
     a.cursor = d_cursor;
     a.cap = cap;
+    a.tile_stride = tile_stride;
     UKM_CUDA(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
-    const int grid = (int)((P.n_bases + KM_TILE - 1) / KM_TILE);
+    const size_t n_tiles = (P.n_bases + KM_TILE - 1) / KM_TILE;
+    const int grid = (int)((n_tiles + tile_stride - 1) / tile_stride);
     {
         ukm_stat_scope st(ctx, P.hashed ? "kmer_nthash_range" : "kmer_encode_range", (double)P.n_bases);
         if (P.hashed) kmer_kernel<true, true><<<grid, KM_THREADS, 0, ctx->stream>>>(a);
@@ -399,20 +403,50 @@ extern "C" int ukm_count_seq(ukm_ctx* ctx, const uint8_t* bases, const uint64_t*
     UKM_TRY(tmp.alloc(&d_cursor, 2));
     const bool out_dev = out->where == UKM_DEVICE;
     cudaMemcpyKind kind = out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    // Codes are not uniform over [0, top] (a canonical hash is the min of two hashes; 2-bit codes follow the base
+    // composition), so the pass boundaries are quantiles of a sample: every `stride`-th tile of start positions
+    // (~4M codes), sorted on the device.
+    std::vector<uint64_t> sample;
+    double sample_frac = 1.0;  // share of the sampled codes that are <= top
+    const bool small = P.total <= ((size_t)32 << 20) && passes == 1;  // everything fits in one pass with cap = total
+    if (!small) {
+        const size_t n_tiles = (P.n_bases + KM_TILE - 1) / KM_TILE;
+        const unsigned stride = (unsigned)std::max<size_t>(1, n_tiles / 128);
+        const size_t scap = (n_tiles / stride + 2) * (size_t)KM_TILE;
+        uint64_t* d_s = nullptr;
+        UKM_TRY(tmp.alloc(&d_s, scap + 2));
+        size_t ns = 0;
+        UKM_TRY(generate_range(ctx, P, 0, top, d_s, scap, d_cursor, &ns, stride));
+        if (ns > scap) ns = scap;
+        if (ns > 1) UKM_TRY(ukm_dev_sort(ctx, d_s, nullptr, ns, key_bits));
+        sample.resize(ns);
+        if (ns) UKM_CUDA(ctx, cudaMemcpyAsync(sample.data(), d_s, ns * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        tmp.free_now(d_s);
+        const double sampled_kmers = (double)P.total / (double)stride;
+        if (sampled_kmers > 0) sample_frac = std::min(1.0, (double)ns / sampled_kmers);
+        passes = (size_t)(((double)P.total * sample_frac + (double)limit - 1) / (double)limit);
+        if (passes < 1) passes = 1;
+    }
     for (int attempt = 0; attempt < 8; ++attempt, passes *= 2) {
-        // per-pass buffers: generous for uniform hashes, retried with twice the passes when a range overflows
-        size_t cap = (size_t)((double)P.total * frac / (double)passes * 1.25) + (1u << 20);
+        // per-pass buffers: 1.3x the expected share, retried with twice the passes when a range still overflows
+        size_t cap = small ? (size_t)P.total : (size_t)((double)P.total * sample_frac / (double)passes * 1.3) + (1u << 20);
         if (cap > P.total) cap = (size_t)P.total;
         uint64_t *d_codes = nullptr, *d_uniq = nullptr;
         UKM_TRY(tmp.alloc(&d_codes, cap + 2));
         UKM_TRY(tmp.alloc(&d_uniq, cap + 2));
         size_t written = 0;
         bool overflow = false;
+        uint64_t lo = 0;
         for (size_t ps = 0; ps < passes && !overflow; ++ps) {
-            // range ps of `passes` over [0, top]
-            const long double width = ((long double)top + 1.0L) / (long double)passes;
-            const uint64_t lo = ps == 0 ? 0 : (uint64_t)(width * (long double)ps);
-            const uint64_t hi = ps + 1 == passes ? top : (uint64_t)(width * (long double)(ps + 1)) - 1;
+            // range ps = (quantile ps/passes, quantile (ps+1)/passes] of the sample; the last range ends at `top`
+            uint64_t hi = top;
+            if (ps + 1 < passes) {
+                if (!sample.empty()) hi = sample[std::min(sample.size() - 1, (size_t)((double)sample.size() * (double)(ps + 1) / (double)passes))];
+                else hi = (uint64_t)(((long double)top + 1.0L) / (long double)passes * (long double)(ps + 1)) - 1;
+                if (hi > top) hi = top;
+            }
+            if (ps > 0 && hi < lo) continue;  // empty range (many equal sample values)
             size_t kept = 0;
             UKM_TRY(generate_range(ctx, P, lo, hi, d_codes, cap, d_cursor, &kept));
             UKM_TRY(ukm_check_dev_error(ctx, "ukm_count_seq"));
@@ -420,17 +454,20 @@ extern "C" int ukm_count_seq(ukm_ctx* ctx, const uint8_t* bases, const uint64_t*
                 overflow = true;
                 break;
             }
-            if (kept == 0) continue;
-            UKM_TRY(ukm_dev_sort(ctx, d_codes, nullptr, kept, key_bits));
-            size_t m = 0;
-            UKM_TRY(ukm_dev_fold(ctx, UKM_FOLD_UNIQUE, d_codes, nullptr, kept, false, d_uniq, nullptr, &m));
-            if (written + m > out->cap) {
-                out->n = written + m;
-                return ukm_fail(ctx, UKM_E_CAPACITY, "ukm_count_seq: output needs more than %zu elements", out->cap);
+            if (kept) {
+                UKM_TRY(ukm_dev_sort(ctx, d_codes, nullptr, kept, key_bits));
+                size_t m = 0;
+                UKM_TRY(ukm_dev_fold(ctx, UKM_FOLD_UNIQUE, d_codes, nullptr, kept, false, d_uniq, nullptr, &m));
+                if (written + m > out->cap) {
+                    out->n = written + m;
+                    return ukm_fail(ctx, UKM_E_CAPACITY, "ukm_count_seq: output needs more than %zu elements", out->cap);
+                }
+                if (m) UKM_CUDA(ctx, cudaMemcpyAsync(out->keys + written, d_uniq, m * sizeof(uint64_t), kind, ctx->stream));
+                UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                written += m;
             }
-            if (m) UKM_CUDA(ctx, cudaMemcpyAsync(out->keys + written, d_uniq, m * sizeof(uint64_t), kind, ctx->stream));
-            UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            written += m;
+            if (hi == top) break;
+            lo = hi + 1;
         }
         tmp.free_now(d_codes);
         tmp.free_now(d_uniq);
