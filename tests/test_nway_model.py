@@ -1,0 +1,21 @@
+"""CPU check of the N-way union arithmetic (unikmer_b200/csrc/nway_core.cuh): the host model
+(tests/host/nway_model.cpp) compiles the header the CUDA kernel uses with g++ and replays the
+kernel's per-thread schedule against std::set_union semantics -- partition by multi-sequence
+selection, merge tables, merge-path splits, plain and de-duplicating walks, every tile shape."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_nway_host_model(tmp_path):
+    exe = tmp_path / "nway_model"
+    src = os.path.join(ROOT, "tests", "host", "nway_model.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", src, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "nway model ok" in out.stdout

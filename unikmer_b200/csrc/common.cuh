@@ -139,6 +139,11 @@ int ukm_dev_fold(ukm_ctx* ctx, int mode, const uint64_t* d_keys, const uint32_t*
 int ukm_dev_fill_u32(ukm_ctx* ctx, uint32_t* d, uint32_t v, size_t n);
 int ukm_dev_check_sorted_unique(ukm_ctx* ctx, const uint64_t* d_keys, size_t n);  // sets the device error word
 
+// single-pass N-way union of 2..8 sorted duplicate-free device arrays (nway.cu)
+bool ukm_nway_enabled();
+int ukm_nway_union(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
+                   bool* fell_back);
+
 static inline int ukm_grid_for(size_t work, int per_block, int sm_count, int max_per_sm = 32) {
     size_t g = (work + per_block - 1) / per_block;
     size_t cap = (size_t)sm_count * max_per_sm;

@@ -1,0 +1,473 @@
+// nway.cu -- single-pass N-way (N <= 8) union of sorted duplicate-free k-mer streams.
+//
+// Replaces the hash-set union of union.go:186-208 and its key sort (union.go:260-305) -- and the levels of the
+// two-way merge tree this library used before -- with ONE pass over the inputs: the key space is cut into tiles
+// of ~TILE elements summed over all files (partition kernels below: multi-sequence selection on
+// rank(K) = sum_f lower_bound(F_f, K), regula falsi + bisection, coarse then fine), every tile is brought into
+// shared memory with one 1-D TMA bulk copy per file and merged there in log2(N) levels of two-way merge-path
+// walks; the last level drops equal neighbours (the same k-mer in several files) and the distinct keys leave
+// through the same deferred, coalesced copy-out as the two-way pipeline (setops.cu).  HBM traffic is the
+// algorithmic minimum: every input byte read once, every output byte written once (a tree of two-way passes
+// moves the data log2(N) times).
+//
+// Kernel shape (persistent, warp-specialised; grid = resident CTAs, tiles round-robin):
+//   warp 0 loader : lane f owns file f -- tile geometry, unaligned head/tail by plain loads, body by TMA
+//                   (cp.async.bulk -> mbarrier complete_tx); lane 0 lays out the merge tables of the tile.
+//   warp 1 prefix : output offsets of the grid iteration (gathers the G counts of tiles [i*G, (i+1)*G)).
+//   warps 2+ consumers: level 1 slot -> X, level 2 X -> slot, last level -> registers (+ unique flags),
+//                   scan, publish count, copy tile i-DEFER out, stage this tile's keys in place.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "nway_core.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// partition kernels: one thread per boundary
+// ---------------------------------------------------------------------------------------------------
+struct NwPartArgs {
+    NwFiles F;
+    long long total;
+    long long tile;  // nominal elements per tile
+    long long tol;   // accepted rank error of a boundary
+    int num_tiles;
+    int nc;          // coarse chunks
+};
+
+__global__ void nway_coarse_kernel(const NwPartArgs a, NwBound* __restrict__ coarse) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > a.nc) return;
+    NwBound lo, hi, out;
+    nw_global_bracket(a.F, &lo, &hi);
+    const long long R = (long long)c * NW_COARSE * a.tile;
+    if (c == 0) out = lo;
+    else if (c == a.nc || R >= a.total) out = hi;
+    else nw_refine(a.F, R, a.tol, lo, hi, &out);
+    coarse[c] = out;
+}
+
+// part[t * NW_MAX + f] = first element of tile t in file f; row num_tiles = the file lengths
+__global__ void nway_fine_kernel(const NwPartArgs a, const NwBound* __restrict__ coarse, long long* __restrict__ part) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > a.num_tiles) return;
+    NwBound out;
+    if (t == a.num_tiles) {
+#pragma unroll
+        for (int f = 0; f < NW_MAX; ++f) out.pos[f] = (f < a.F.nf) ? a.F.n[f] : 0;
+    } else {
+        const int c = t / NW_COARSE;
+        if (t % NW_COARSE == 0) out = coarse[c];
+        else nw_refine(a.F, (long long)t * a.tile, a.tol, coarse[c], coarse[c + 1], &out);
+    }
+#pragma unroll
+    for (int f = 0; f < NW_MAX; ++f) part[(size_t)t * NW_MAX + f] = out.pos[f];
+}
+
+// every tile must fit the shared-memory slot (it does for duplicate-free inputs); info[0] = bad flag, info[1] = largest tile
+__global__ void nway_check_kernel(const long long* __restrict__ part, int num_tiles, int cap, int* __restrict__ info) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    long long sum = 0;
+    bool bad = false;
+#pragma unroll
+    for (int f = 0; f < NW_MAX; ++f) {
+        const long long d = part[(size_t)(t + 1) * NW_MAX + f] - part[(size_t)t * NW_MAX + f];
+        if (d < 0) bad = true;
+        sum += d;
+    }
+    if (sum > cap) bad = true;
+    if (bad) atomicExch(&info[0], 1);
+    if (sum > 0x7fffffff) sum = 0x7fffffff;
+    atomicMax(&info[1], (int)sum);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the tile kernel
+// ---------------------------------------------------------------------------------------------------
+constexpr int NWK_MAX_GRID = 512;  // prefix warp keeps NWK_MAX_GRID/32 counts per lane
+constexpr int NWK_AUX = 64;        // loader + prefix warps
+
+struct NwArgs {
+    NwFiles F;
+    const long long* part;
+    uint64_t* outK;
+    uint64_t* status;  // one count word per tile (flag << 62 | count)
+    unsigned long long* total_out;
+    int num_tiles;
+    int* err;
+};
+
+// 16-byte alignment helpers for the 1-D bulk copies (same contract as slice_* in setops.cu): element
+// start+i of g lands in s[h + i], h = misalignment of g+start in elements; s is 16-byte aligned.
+__device__ __forceinline__ int nw_slice_h(const uint64_t* g, long long start) {
+    return (int)((reinterpret_cast<uintptr_t>(g + start) & 15u) >> 3);
+}
+
+template <int NWAY, int NT, int VT>
+struct NwShape {
+    static constexpr int CAP = (NT - NWAY / 2) * VT;               // most elements a tile may hold
+    static constexpr int SLOT_E = (CAP + 2 * NWAY + 8 + 1) & ~1;   // + per-segment alignment slack + read-past padding
+    static constexpr int X_E = (CAP + 8 + 1) & ~1;
+    static constexpr int TILE = (CAP * 16 / 17) & ~31;             // nominal tile; boundaries are exact to +-TILE/32
+    static constexpr int LEVELS = NwGeom<NWAY>::LEVELS;
+};
+
+template <int NWAY, int NT, int VT, int SLOTS, int MINB>
+__global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_union_kernel(const NwArgs p) {
+    using SH = NwShape<NWAY, NT, VT>;
+    constexpr int NW = NT / 32;
+    constexpr int DEFER = SLOTS - 2;
+    constexpr int LEVELS = SH::LEVELS;
+    extern __shared__ __align__(16) unsigned char nw_smem[];
+    uint64_t* s_slots = reinterpret_cast<uint64_t*>(nw_smem);  // SLOTS * SLOT_E
+    uint64_t* s_x = s_slots + (size_t)SLOTS * SH::SLOT_E;      // X_E
+    __shared__ __align__(8) uint64_t full_bar[SLOTS], empty_bar[SLOTS], pre_bar[SLOTS];
+    __shared__ unsigned long long s_cnt[SLOTS], s_pre[SLOTS];
+    __shared__ NwGeom<NWAY> s_geom[SLOTS];
+    __shared__ const uint64_t* s_fk[NW_MAX];
+    __shared__ unsigned s_scan[NW + 2];
+
+    const int G = gridDim.x;
+    const int n_my = (p.num_tiles - (int)blockIdx.x + G - 1) / G;  // tiles of this CTA
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SLOTS; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NT);
+            mbar_init(&pre_bar[s], 1);
+        }
+#pragma unroll
+        for (int f = 0; f < NW_MAX; ++f) s_fk[f] = p.F.k[f];
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const unsigned lane = lane_id();
+
+    if (threadIdx.x < 32) {
+        // ================= loader warp: lane f owns file f =================
+        const uint64_t* fk = lane < NWAY ? s_fk[lane] : nullptr;
+        for (int li = 0; li < n_my; ++li) {
+            const int s = li % SLOTS, u = li / SLOTS;
+            if (u > 0 && !mbar_wait(&empty_bar[s], (unsigned)(u - 1) & 1u)) {
+                if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+            }
+            const int tile = (int)blockIdx.x + li * G;
+            long long lo = 0;
+            int n = 0;
+            if (lane < NWAY) {
+                lo = p.part[(size_t)tile * NW_MAX + lane];
+                const long long hi = p.part[(size_t)(tile + 1) * NW_MAX + lane];
+                n = (int)(hi - lo);
+            }
+            int sum = n;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+            const bool bad = __any_sync(0xffffffffu, n < 0) || sum > SH::CAP;  // cannot happen after nway_check
+            if (bad) {
+                if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+                n = 0;
+            }
+            const int h = (n > 0) ? nw_slice_h(fk, lo) : 0;
+            const int padded = (h + n + 1) & ~1;
+            int incl = padded;  // inclusive scan over the lanes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += v;
+            }
+            const int base = incl - padded;  // even
+            uint64_t* slot = s_slots + (size_t)s * SH::SLOT_E;
+            // 16-byte aligned body through TMA, the (at most one element) head and tail through plain loads
+            int head = 0, body = 0;
+            if (n > 0) {
+                head = h ? 1 : 0;
+                body = (n - head) & ~1;
+                if (head) slot[base + h] = fk[lo];
+                if (head + body < n) slot[base + h + n - 1] = fk[lo + n - 1];
+            }
+            unsigned bytes = (unsigned)body * 8u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
+            if (lane < NWAY) {
+                s_geom[s].n[lane] = n;
+                s_geom[s].off[lane] = base + h;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                nw_build_tables<NWAY, VT>(&s_geom[s]);
+                mbar_expect_tx(&full_bar[s], bytes);  // arrive (release: publishes the plain stores and the tables) + tx count
+            }
+            __syncwarp();
+            if (body) tma_load_1d(slot + base + h + head, fk + lo + head, (unsigned)body * 8u, &full_bar[s]);
+        }
+        return;
+    }
+    if (threadIdx.x < 64) {
+        // ================= prefix warp (same scheme as setop_pipe_kernel) =================
+        constexpr int MAXM = NWK_MAX_GRID / 32;
+        unsigned long long P = 0;  // outputs of all earlier grid iterations (identical on every CTA)
+        for (int bi = 0; bi < n_my; ++bi) {
+            const int s = bi % SLOTS;
+            const int tile0 = bi * G;
+            const int n_iter = (p.num_tiles - tile0) < G ? (p.num_tiles - tile0) : G;
+            unsigned long long val[MAXM];
+            unsigned have = 0;
+            unsigned spins = 0;
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) {
+                val[m] = 0;
+                if ((int)lane + 32 * m >= n_iter) have |= 1u << m;
+            }
+            while (true) {
+#pragma unroll
+                for (int m = 0; m < MAXM; ++m) {
+                    if (!(have & (1u << m))) {
+                        const uint64_t w = ld_relaxed_u64(&p.status[tile0 + (int)lane + 32 * m]);
+                        if (w >> 62) {
+                            val[m] = UKM_LB_VALUE(w);
+                            have |= 1u << m;
+                        }
+                    }
+                }
+                if (__all_sync(0xffffffffu, have == ((1u << MAXM) - 1))) break;
+                __nanosleep(100);
+                if (++spins > UKM_WATCHDOG_SPINS) {
+                    if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+                    break;
+                }
+            }
+            unsigned long long before = 0, all = 0;
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) {
+                all += val[m];
+                if ((int)lane + 32 * m < (int)blockIdx.x) before += val[m];
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                before += __shfl_xor_sync(0xffffffffu, before, d);
+                all += __shfl_xor_sync(0xffffffffu, all, d);
+            }
+            if (lane == 0) {
+                s_pre[s] = P + before;
+                if (tile0 + n_iter == p.num_tiles && (int)blockIdx.x == n_iter - 1) *p.total_out = P + all;
+                mbar_arrive(&pre_bar[s]);
+            }
+            P += all;
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ================= consumers =================
+    const int tid = (int)threadIdx.x - NWK_AUX;
+    for (int i = 0; i < n_my + DEFER; ++i) {
+        unsigned emitmask = 0;
+        uint64_t outk[VT];
+        unsigned off = 0;
+        uint64_t* slot = nullptr;
+        if (i < n_my) {
+            const int s = i % SLOTS, u = i / SLOTS;
+            slot = s_slots + (size_t)s * SH::SLOT_E;
+            if (!mbar_wait(&full_bar[s], (unsigned)u & 1u)) {
+                if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+            }
+            const NwGeom<NWAY>& g = s_geom[s];
+            const uint64_t* src = slot;
+            uint64_t* dst = s_x;
+            // inner levels: plain two-way merges, every pair of runs by its own group of threads
+#pragma unroll
+            for (int l = 1; l < LEVELS; ++l) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int npairs = NWAY >> l;
+                const int p0 = nw_pair0<NWAY>(l), t0 = nw_tb0<NWAY>(l);
+                int j = 0, m;
+                if (npairs == 4) m = nw_find_pair<4>(g.tb + t0, tid, &j);
+                else m = nw_find_pair<2>(g.tb + t0, tid, &j);
+                if (m >= 0) {
+                    const NwPair pr = g.pair[p0 + m];
+                    const int diag = j * VT;
+                    int steps = pr.lenA + pr.lenB - diag;
+                    if (steps > VT) steps = VT;
+                    const uint64_t* A = src + pr.srcA;
+                    const uint64_t* B = src + pr.srcB;
+                    const int a = nw_merge_path(A, pr.lenA, B, pr.lenB, diag);
+                    nw_walk_plain<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, dst + pr.dst + diag);
+                }
+                named_bar_sync(1, NT);
+                // level 1: slot -> X; level 2: X -> slot
+                const uint64_t* t = src;
+                src = dst;
+                dst = const_cast<uint64_t*>(t);
+            }
+            // last level: merge into registers, keep the first key of every run of equal keys
+            {
+                const NwPair pr = g.pair[NWAY - 2];
+                const int tot = pr.lenA + pr.lenB;
+                int diag = tid * VT;
+                int steps = tot - diag;
+                if (steps > VT) steps = VT;
+                if (diag > tot) diag = tot;
+                const uint64_t* A = src + pr.srcA;
+                const uint64_t* B = src + pr.srcB;
+                const int a = nw_merge_path(A, pr.lenA, B, pr.lenB, diag);
+                emitmask = nw_walk_unique<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, outk);
+            }
+            unsigned tile_total;
+            off = group_excl_scan_u32<NT>((unsigned)__popc(emitmask), (unsigned)tid, s_scan, &tile_total, 1);
+            // every consumer is past its reads of the slot (two barriers inside the scan): it may be overwritten
+            if (tid == 0) {
+                s_cnt[s] = tile_total;
+                st_relaxed_u64(&p.status[(int)blockIdx.x + i * G], UKM_LB_PARTIAL | (uint64_t)tile_total);
+            }
+        }
+        // copy tile i-DEFER out while this tile's count travels
+        if (i >= DEFER && i - DEFER < n_my) {
+            const int ip = i - DEFER;
+            const int sp = ip % SLOTS, up = ip / SLOTS;
+            const uint64_t* prev = s_slots + (size_t)sp * SH::SLOT_E;
+            if (!mbar_wait(&pre_bar[sp], (unsigned)up & 1u)) {
+                if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+            }
+            const unsigned long long prefix = s_pre[sp];
+            const unsigned n_prev = (unsigned)s_cnt[sp];
+            uint64_t* out = p.outK + prefix;
+            for (unsigned j = tid; j < n_prev; j += NT) out[j] = prev[j];
+            mbar_arrive(&empty_bar[sp]);  // release: my reads of the slot are done
+        }
+        // stage this tile's distinct keys in place
+        if (i < n_my) {
+            unsigned o = off;
+#pragma unroll
+            for (int it = 0; it < VT; ++it) {
+                if (emitmask & (1u << it)) slot[o++] = outk[it];
+            }
+        }
+        named_bar_sync(1, NT);  // staged tile (and s_cnt) visible to every consumer before a later copy-out
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+template <int NWAY, int NT, int VT, int SLOTS, int MINB>
+int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_back) {
+    using SH = NwShape<NWAY, NT, VT>;
+    constexpr size_t smem = ((size_t)SLOTS * SH::SLOT_E + SH::X_E) * 8;
+    auto kern = nway_union_kernel<NWAY, NT, VT, SLOTS, MINB>;
+    static int ctas_per_sm = 0;  // per instantiation
+    if (ctas_per_sm == 0) {
+        UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT + NWK_AUX, smem));
+        if (nb < 1) return ukm_fail(ctx, UKM_E_INTERNAL, "nway_union_kernel does not fit on an SM");
+        ctas_per_sm = nb;
+    }
+    // ---- partition: tiles of ~TILE elements summed over all files ----
+    pa.tile = SH::TILE;
+    pa.tol = SH::TILE / 32;
+    const int num_tiles = (int)((pa.total + SH::TILE - 1) / SH::TILE);
+    pa.num_tiles = num_tiles;
+    pa.nc = (num_tiles + NW_COARSE - 1) / NW_COARSE;
+    NwBound* d_coarse = nullptr;
+    long long* d_part = nullptr;
+    uint64_t* d_status = nullptr;
+    UKM_TRY(tmp.alloc(&d_coarse, (size_t)pa.nc + 1));
+    UKM_TRY(tmp.alloc(&d_part, (size_t)(num_tiles + 1) * NW_MAX));
+    UKM_TRY(tmp.alloc(&d_status, (size_t)num_tiles + 4));
+    // output total and the check words live in the tail of the status allocation (zeroed together)
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(d_status + num_tiles);
+    int* d_info = reinterpret_cast<int*>(d_status + num_tiles + 1);
+    UKM_CUDA(ctx, cudaMemsetAsync(d_status, 0, ((size_t)num_tiles + 4) * sizeof(uint64_t), ctx->stream));
+    nway_coarse_kernel<<<(pa.nc + 1 + 63) / 64, 64, 0, ctx->stream>>>(pa, d_coarse);
+    UKM_LAUNCHED(ctx);
+    nway_fine_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(pa, d_coarse, d_part);
+    UKM_LAUNCHED(ctx);
+    nway_check_kernel<<<(num_tiles + 127) / 128, 128, 0, ctx->stream>>>(d_part, num_tiles, SH::CAP, d_info);
+    UKM_LAUNCHED(ctx);
+    UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_info, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (reinterpret_cast<int*>(ctx->h_scratch)[0] != 0) {
+        *fell_back = true;  // some key occurs far too often for a tile: inputs are not duplicate-free
+        return UKM_OK;
+    }
+    a.part = d_part;
+    a.status = d_status;
+    a.total_out = d_total;
+    a.num_tiles = num_tiles;
+    int grid = ctas_per_sm * ctx->sm_count;
+    if (grid > NWK_MAX_GRID) grid = NWK_MAX_GRID;
+    if (grid > num_tiles) grid = num_tiles;
+    kern<<<grid, NT + NWK_AUX, smem, ctx->stream>>>(a);
+    UKM_LAUNCHED(ctx);
+    UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tmp.free_now(d_coarse);
+    tmp.free_now(d_part);
+    tmp.free_now(d_status);
+    return UKM_OK;
+}
+
+// tile shapes: consumer threads x keys per thread x ring slots.  UKM_NWAY_CFG picks one by index for A/B runs.
+int nway_cfg() {
+    const char* e = getenv("UKM_NWAY_CFG");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 0 && v < 4) ? v : 0;
+}
+
+template <int NWAY>
+int launch_nway_cfg(ukm_ctx* ctx, const NwArgs& a, const NwPartArgs& pa, ukm_tmp& tmp, bool* fell_back) {
+    switch (nway_cfg()) {
+        case 1: return launch_nway<NWAY, 128, 17, 3, 3>(ctx, a, pa, tmp, fell_back);
+        case 2: return launch_nway<NWAY, 256, 13, 3, 2>(ctx, a, pa, tmp, fell_back);
+        case 3: return launch_nway<NWAY, 128, 17, 4, 2>(ctx, a, pa, tmp, fell_back);
+        default: return launch_nway<NWAY, 256, 9, 3, 3>(ctx, a, pa, tmp, fell_back);
+    }
+}
+
+}  // namespace
+
+bool ukm_nway_enabled() {
+    const char* e = getenv("UKM_NWAY");
+    return !(e && e[0] == '0');
+}
+
+// Union of nf (2..8) sorted duplicate-free device arrays into outK (capacity >= sum of the lengths).
+// *fell_back = true (and nothing written) when the inputs cannot be tiled -- the caller then uses the
+// two-way tree, which takes any input.
+int ukm_nway_union(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
+                   bool* fell_back) {
+    *fell_back = false;
+    *n_out = 0;
+    if (nf < 2 || nf > NW_MAX) return ukm_fail(ctx, UKM_E_ARG, "ukm_nway_union: 2..8 inputs");
+    NwArgs a;
+    NwPartArgs pa;
+    long long total = 0;
+    for (int f = 0; f < NW_MAX; ++f) {
+        a.F.k[f] = f < nf ? keys[f] : nullptr;
+        a.F.n[f] = f < nf ? (long long)n[f] : 0;
+        total += a.F.n[f];
+    }
+    a.F.nf = nf;
+    if (total == 0) return UKM_OK;
+    pa.F = a.F;
+    pa.total = total;
+    a.outK = outK;
+    a.err = ctx->d_err;
+    ukm_tmp tmp(ctx);
+    {
+        ukm_stat_scope st(ctx, "setop_union_nway", (double)total * 8.0);
+        int r;
+        if (nf <= 2) r = launch_nway_cfg<2>(ctx, a, pa, tmp, fell_back);
+        else if (nf <= 4) r = launch_nway_cfg<4>(ctx, a, pa, tmp, fell_back);
+        else r = launch_nway_cfg<8>(ctx, a, pa, tmp, fell_back);
+        UKM_TRY(r);
+    }
+    if (*fell_back) {
+        if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes = 0;
+        return UKM_OK;
+    }
+    *n_out = (size_t)ctx->h_scratch[0];
+    if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes += (double)*n_out * 8.0;
+    return UKM_OK;
+}

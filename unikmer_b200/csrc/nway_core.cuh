@@ -1,0 +1,273 @@
+// nway_core.cuh -- the arithmetic of the N-way (N <= 8) single-pass union, written so that the same
+// functions run inside the CUDA kernel (nway.cu) and, compiled by g++, inside the host model that the
+// CPU test-suite drives (tests/host/nway_model.cpp): tile partition by key (multi-sequence selection on
+// rank(K) = sum_f lower_bound(F_f, K)), per-tile run tables, merge-path split, the plain two-way walk of the
+// inner levels and the de-duplicating walk of the last level.
+//
+// What it replaces: the hash-set union of union.go:186-208 + the key sort of union.go:260-305 (and, as
+// the merge step, mergeChunksFile's heap, util-sort.go:227-606) -- here every input is read ONCE: a tile
+// of the key space is brought into shared memory from all N files and merged there in log2(N) levels.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define NW_HD __host__ __device__ __forceinline__
+#else
+#define NW_HD inline
+#endif
+
+constexpr int NW_MAX = 8;       // files per pass
+constexpr int NW_COARSE = 32;   // tiles per coarse partition chunk
+constexpr int NW_MAX_PAIRS = 7; // 4 + 2 + 1 two-way merges per tile at N = 8
+
+// ---------------------------------------------------------------------------------------------------
+// partition: cut every file at lower_bound(key); rank = total elements below the cut
+// ---------------------------------------------------------------------------------------------------
+struct NwBound {
+    uint64_t key;
+    long long rank;
+    long long pos[NW_MAX];
+};
+
+struct NwFiles {
+    const uint64_t* k[NW_MAX];
+    long long n[NW_MAX];
+    int nf;  // files in use (the others have n = 0)
+};
+
+NW_HD long long nw_lower_bound(const uint64_t* F, long long lo, long long hi, uint64_t key) {
+    while (lo < hi) {
+        const long long mid = lo + ((hi - lo) >> 1);
+        if (F[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// mid = the cut at `key`: pos[f] = lower_bound(F_f, key) searched inside [lo.pos[f], hi.pos[f]].  The eight
+// bisections advance in lock step so that their (dependent, long-latency) loads are in flight together.
+NW_HD void nw_cut_at(const NwFiles& F, uint64_t key, const NwBound& lo, const NwBound& hi, NwBound* mid) {
+    long long p[NW_MAX], n[NW_MAX];
+    long long maxn = 0;
+#pragma unroll
+    for (int f = 0; f < NW_MAX; ++f) {
+        p[f] = lo.pos[f];
+        n[f] = (f < F.nf) ? hi.pos[f] - lo.pos[f] : 0;  // the answer lies in [p, p + n]
+        if (n[f] > maxn) maxn = n[f];
+    }
+    while (maxn > 0) {
+        uint64_t v[NW_MAX];
+#pragma unroll
+        for (int f = 0; f < NW_MAX; ++f) v[f] = (n[f] > 0) ? F.k[f][p[f] + (n[f] >> 1)] : 0;
+#pragma unroll
+        for (int f = 0; f < NW_MAX; ++f) {
+            if (n[f] > 0) {
+                const long long half = n[f] >> 1;
+                if (v[f] < key) { p[f] += half + 1; n[f] -= half + 1; }
+                else n[f] = half;
+            }
+        }
+        maxn >>= 1;
+    }
+    mid->key = key;
+    mid->rank = 0;
+#pragma unroll
+    for (int f = 0; f < NW_MAX; ++f) {
+        mid->pos[f] = p[f];
+        mid->rank += p[f];
+    }
+}
+
+// Find a cut whose rank is within `tol` of R, given a bracket lo.rank <= R <= hi.rank (lo.key <= hi.key;
+// hi may be the end-of-everything boundary: pos = n).  Multi-sequence selection with pivots taken from the
+// DATA, so it does not care how the keys are spread over the key space: the pivot is the element at the
+// wanted rank fraction of the file with the widest position bracket (even rounds; one to three rounds on real
+// inputs) or that bracket's median (odd rounds; bounds the worst case at ~2 * 8 * log2(n) rounds).  Every
+// round searches only inside the per-file position brackets, which shrink with the key bracket.  If no cut
+// lands within tol (needs a key that occurs more than tol times, i.e. inputs that are not duplicate-free,
+// or tol < 8) the upper end of the final bracket is returned; nway_check validates the tile sizes.
+NW_HD void nw_refine(const NwFiles& F, long long R, long long tol, NwBound lo, NwBound hi, NwBound* out) {
+    if (R - lo.rank <= tol) { *out = lo; return; }
+    if (hi.rank - R <= tol) { *out = hi; return; }
+    for (int round = 0; round < 1024; ++round) {
+        int fs = 0;
+        long long w = -1;
+#pragma unroll
+        for (int f = 0; f < NW_MAX; ++f) {
+            const long long wf = hi.pos[f] - lo.pos[f];
+            if (wf > w) { w = wf; fs = f; }
+        }
+        if (w < 2) break;
+        long long d;
+        if (round & 1) {
+            d = w >> 1;
+        } else {
+            const double frac = (double)(R - lo.rank) / (double)(hi.rank - lo.rank);
+            d = (long long)(frac * (double)w);
+        }
+        if (d < 1) d = 1;
+        if (d > w - 1) d = w - 1;
+        const uint64_t* Fs = F.k[0];
+        long long lofs = lo.pos[0];
+#pragma unroll
+        for (int f = 1; f < NW_MAX; ++f)
+            if (f == fs) { Fs = F.k[f]; lofs = lo.pos[f]; }
+        NwBound mid;
+        nw_cut_at(F, Fs[lofs + d], lo, hi, &mid);  // lo.key < mid.key < hi.key: strictly inside the bracket
+        const long long err = mid.rank - R;
+        if (err >= -tol && err <= tol) { *out = mid; return; }
+        if (err < 0) lo = mid;
+        else hi = mid;
+    }
+    *out = hi;
+}
+
+// the bracket that holds everything: [cut below every key, cut above every key]
+NW_HD void nw_global_bracket(const NwFiles& F, NwBound* lo, NwBound* hi) {
+    uint64_t kmin = ~0ull, kmax = 0;
+    long long total = 0;
+    for (int f = 0; f < NW_MAX; ++f) {
+        lo->pos[f] = 0;
+        hi->pos[f] = (f < F.nf) ? F.n[f] : 0;
+        if (f < F.nf && F.n[f] > 0) {
+            const uint64_t a = F.k[f][0], b = F.k[f][F.n[f] - 1];
+            if (a < kmin) kmin = a;
+            if (b > kmax) kmax = b;
+            total += F.n[f];
+        }
+    }
+    if (kmin > kmax) kmin = kmax = 0;  // nothing at all
+    lo->key = kmin;  // lower_bound(kmin) = 0 in every file
+    lo->rank = 0;
+    hi->key = kmax;  // stands for "above kmax": candidate cuts are lo.key < K < kmax
+    hi->rank = total;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-tile geometry: where the N segments sit in the slot, and the two-way merges of every level
+// ---------------------------------------------------------------------------------------------------
+struct NwPair {
+    int srcA, lenA, srcB, lenB;  // runs in the source buffer of the level
+    int dst;                     // start of the merged run in the destination buffer (dense)
+};
+
+template <int NWAY>
+struct NwGeom {
+    static constexpr int LEVELS = NWAY == 8 ? 3 : NWAY == 4 ? 2 : 1;
+    int n[NWAY];    // segment lengths
+    int off[NWAY];  // first element of segment f in the slot
+    int tot;
+    NwPair pair[NWAY - 1];  // level 1 pairs first (NWAY/2), then level 2, ...; the last entry is the final merge
+    int tb[NWAY - 1 + 3];   // thread bases: for level l, tb[tbo(l) + m] .. ; one extra end entry per level
+};
+
+// index of the first pair / first thread-base entry of level l (1-based)
+template <int NWAY>
+NW_HD int nw_pair0(int l) {
+    int p = 0, m = NWAY / 2;
+    for (int i = 1; i < l; ++i) { p += m; m >>= 1; }
+    return p;
+}
+template <int NWAY>
+NW_HD int nw_tb0(int l) { return nw_pair0<NWAY>(l) + (l - 1); }
+
+// Fill pair[] and tb[] from n[] / off[].  Level 1 reads the slot (segments at off[]), every later level
+// reads the dense output of the level before.
+template <int NWAY, int VT>
+NW_HD void nw_build_tables(NwGeom<NWAY>* g) {
+    constexpr int LEVELS = NwGeom<NWAY>::LEVELS;
+    int start[NWAY], len[NWAY];
+    int tot = 0;
+    for (int f = 0; f < NWAY; ++f) { start[f] = g->off[f]; len[f] = g->n[f]; tot += g->n[f]; }
+    g->tot = tot;
+    int runs = NWAY;
+#pragma unroll
+    for (int l = 1; l <= LEVELS; ++l) {
+        const int p0 = nw_pair0<NWAY>(l), t0 = nw_tb0<NWAY>(l);
+        int dst = 0, tbase = 0;
+#pragma unroll
+        for (int m = 0; m < NWAY / 2; ++m) {
+            if (m >= runs / 2) break;
+            NwPair& pr = g->pair[p0 + m];
+            pr.srcA = start[2 * m]; pr.lenA = len[2 * m];
+            pr.srcB = start[2 * m + 1]; pr.lenB = len[2 * m + 1];
+            pr.dst = dst;
+            g->tb[t0 + m] = tbase;
+            const int s = pr.lenA + pr.lenB;
+            start[m] = dst; len[m] = s;  // run m of the next level (m <= 2m: not yet consumed entries stay intact)
+            dst += s;
+            tbase += (s + VT - 1) / VT;
+        }
+        g->tb[t0 + runs / 2] = tbase;
+        runs >>= 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// merge path + walks
+// ---------------------------------------------------------------------------------------------------
+// number of A elements among the first `diag` merged elements; ties: A first
+NW_HD int nw_merge_path(const uint64_t* A, int na, const uint64_t* B, int nb, int diag) {
+    int lo = diag > nb ? diag - nb : 0;
+    int hi = diag < na ? diag : na;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (A[mid] <= B[diag - 1 - mid]) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// which pair of a level does thread `tid` work on (-1: none), and its index inside the pair
+template <int NPAIRS>
+NW_HD int nw_find_pair(const int* tb, int tid, int* j) {
+    if (tid >= tb[NPAIRS]) return -1;
+    int m = 0;
+#pragma unroll
+    for (int i = 1; i < NPAIRS; ++i) m += (tid >= tb[i]) ? 1 : 0;
+    *j = tid - tb[m];
+    return m;
+}
+
+// plain two-way merge of `steps` (<= VT) elements starting at split (a, b): dst[0..steps)
+// (A[na] / B[nb] may be read but are never used: every buffer carries padding behind its last run)
+template <int VT>
+NW_HD void nw_walk_plain(const uint64_t* A, int na, const uint64_t* B, int nb, int a, int b, int steps, uint64_t* dst) {
+    uint64_t ka = A[a], kb = B[b];
+#pragma unroll
+    for (int it = 0; it < VT; ++it) {
+        if (it < steps) {
+            const bool takeA = (a < na) && (b >= nb || ka <= kb);
+            dst[it] = takeA ? ka : kb;
+            if (takeA) ka = A[++a];
+            else kb = B[++b];
+        }
+    }
+}
+
+// last level: merge into registers, flag the first element of every run of equal keys.
+// Returns the emit mask (bit it = outk[it] is a new distinct key).
+template <int VT>
+NW_HD unsigned nw_walk_unique(const uint64_t* A, int na, const uint64_t* B, int nb, int a, int b, int steps, uint64_t* outk) {
+    bool has_prev = (a > 0) || (b > 0);
+    uint64_t prev = 0;
+    if (a > 0) prev = A[a - 1];
+    if (b > 0 && B[b - 1] > prev) prev = B[b - 1];
+    uint64_t ka = A[a], kb = B[b];
+    unsigned mask = 0;
+#pragma unroll
+    for (int it = 0; it < VT; ++it) {
+        const bool takeA = (a < na) && (b >= nb || ka <= kb);
+        const uint64_t k = takeA ? ka : kb;
+        outk[it] = k;
+        const bool emit = (it < steps) && (!has_prev || k != prev);
+        mask |= (emit ? 1u : 0u) << it;
+        prev = k;
+        has_prev = true;
+        if (it < steps) {
+            if (takeA) ka = A[++a];
+            else kb = B[++b];
+        }
+    }
+    return mask;
+}

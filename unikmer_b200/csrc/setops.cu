@@ -18,6 +18,8 @@
 #include "common.cuh"
 #include "lca.cuh"
 
+constexpr int NW_FANIN = 8;  // sets per pass of the N-way union (nway.cu)
+
 namespace {
 
 enum SetOp { OP_INTER = 0, OP_DIFF = 1, OP_UNION = 2, OP_MERGE = 3 };
@@ -1157,33 +1159,64 @@ int run_tree(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags,
         level.push_back(DevSet());
         src.push_back(-2);
     }
+    // keys-only unions go through the single-pass N-way kernel (nway.cu), up to 8 sets per pass
+    bool nway = op == OP_UNION && !tax && !cnt && ukm_nway_enabled();
     while (level.size() > 1) {
         std::vector<DevSet> next;
         std::vector<int> nsrc;
-        const bool last = level.size() == 2;
-        for (size_t i = 0; i + 1 < level.size(); i += 2) {
+        const size_t fan = nway ? (size_t)NW_FANIN : 2;
+        const bool last = level.size() <= fan;
+        for (size_t i = 0; i < level.size(); i += fan) {
+            const size_t gsz = level.size() - i < fan ? level.size() - i : fan;
+            if (gsz == 1) {
+                next.push_back(level[i]);
+                nsrc.push_back(src[i]);
+                continue;
+            }
             DevSet o;
-            const size_t bound = level[i].n + level[i + 1].n;
+            size_t bound = 0;
+            for (size_t j = i; j < i + gsz; ++j) bound += level[j].n;
+            bool direct = false;
             if (last && fold_mode == UKM_FOLD_PLAIN && out->where == UKM_DEVICE && out->cap >= bound && out->keys &&
                 (!tax || out->taxids)) {
                 // final pass writes straight into the caller's device buffers (no extra copy)
                 o.k = out->keys;
                 o.t = tax ? out->taxids : nullptr;
                 if (cnt) UKM_TRY(tmp.alloc(&o.c, bound + 4));
+                direct = true;
             } else {
                 UKM_TRY(alloc_set(tmp, &o, bound, tax, cnt));
             }
-            UKM_TRY(setop2(ctx, op, level[i], level[i + 1], tax, cnt, flags, last ? threshold : 0, &o));
-            for (size_t j = i; j < i + 2; ++j) {
+            if (nway) {
+                const uint64_t* ks[NW_FANIN];
+                size_t ns[NW_FANIN];
+                for (size_t j = 0; j < gsz; ++j) {
+                    ks[j] = level[i + j].k;
+                    ns[j] = level[i + j].n;
+                }
+                bool fell_back = false;
+                size_t n_o = 0;
+                UKM_TRY(ukm_nway_union(ctx, ks, ns, (int)gsz, o.k, &n_o, &fell_back));
+                if (fell_back) {
+                    // inputs that cannot be tiled (not duplicate-free): the rest of the tree runs two-way passes
+                    if (!direct) free_set(tmp, &o);
+                    for (size_t j = i; j < level.size(); ++j) {
+                        next.push_back(level[j]);
+                        nsrc.push_back(src[j]);
+                    }
+                    nway = false;
+                    break;
+                }
+                o.n = n_o;
+            } else {
+                UKM_TRY(setop2(ctx, op, level[i], level[i + 1], tax, cnt, flags, last ? threshold : 0, &o));
+            }
+            for (size_t j = i; j < i + gsz; ++j) {
                 if (src[j] >= 0) unstage_set(tmp, &in[src[j]], &level[j]);
                 else if (src[j] == -1) free_set(tmp, &level[j]);
             }
             next.push_back(o);
             nsrc.push_back(-1);
-        }
-        if (level.size() & 1) {
-            next.push_back(level.back());
-            nsrc.push_back(src.back());
         }
         level.swap(next);
         src.swap(nsrc);
