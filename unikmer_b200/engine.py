@@ -185,6 +185,21 @@ class Engine:
         n = int(sp.n)
         return k[:n], (None if t is None else t[:n])
 
+    def upload(self, host):
+        """Copy a host array (numpy, or a pinned CPU torch tensor) of 64-bit codes into a new device tensor through
+        ukm_copy: the returned tensor is a DEVICE span for any later operation (ops then chain without PCIe traffic)."""
+        import torch
+        if _is_torch(host):
+            assert not host.is_cuda and host.is_contiguous() and host.element_size() == 8
+            n, ptr, where = host.shape[0], host.data_ptr(), L.HOST_PINNED
+            keep = host
+        else:
+            keep = self._host_u64(host)
+            n, ptr, where = len(keep), keep.ctypes.data, L.HOST
+        d = torch.empty(n, dtype=torch.int64, device=f"cuda:{self.device}")
+        self._chk(self.lib.ukm_copy(self.ctx, d.data_ptr(), L.DEVICE, ptr, where, n * 8))
+        return d
+
     # ---- taxonomy (util.go:119-171) ---------------------------------------------------
     def set_taxonomy(self, parent, merged_from=None, merged_to=None):
         p = self._host_u32(parent)
