@@ -88,15 +88,27 @@ def test_nway_union_misaligned_device_pointers(eng):
     same(got.cpu().numpy().view(U64), exp, "misaligned union")
 
 
-def test_nway_union_falls_back_on_inputs_that_cannot_be_tiled(eng):
-    """One key repeated far beyond a tile (not duplicate-free: outside the contract) must not be mis-merged:
-    the partition refuses and the two-way tree runs, as it did before."""
+def test_nway_union_falls_back_on_inputs_that_cannot_be_tiled(eng, monkeypatch):
+    """One key repeated far beyond a tile (not duplicate-free: outside the contract) must never be mis-merged: the
+    partition refuses the input and the two-way tree takes over, which behaves as it always did -- it either reports
+    UKM_E_NOT_SORTED_UNIQUE (a tile seam fell inside the run of duplicates) or returns the merged keys."""
+    import unikmer_b200 as ub
     r = rng(3)
     files = []
     for f in range(8):
         a = np.unique(r.integers(0, 2**40, 20_000, dtype=U64))
         files.append(np.concatenate([a, np.full(5_000, 2**41, dtype=U64)]))
-    got = eng.union(files)[0]
-    # the two-way walk keeps intra-file duplicates (multiset semantics); distinct keys and order are what matter here
-    assert np.array_equal(np.unique(got), exp_union(files))
-    assert bool((got[1:] >= got[:-1]).all())
+
+    def run():
+        try:
+            return eng.union(files)[0]
+        except ub.UkmError as e:
+            assert e.status == ub.E_NOT_SORTED_UNIQUE
+            return None
+    got = run()
+    monkeypatch.setenv("UKM_NWAY", "0")
+    old = run()
+    assert (got is None) == (old is None)
+    if got is not None:
+        same(got, old, "fallback result = two-way tree result")
+        assert np.array_equal(np.unique(got), exp_union(files))

@@ -233,14 +233,25 @@ NW_HD int nw_find_pair(const int* tb, int tid, int* j) {
 // (A[na] / B[nb] may be read but are never used: every buffer carries padding behind its last run)
 template <int VT>
 NW_HD void nw_walk_plain(const uint64_t* A, int na, const uint64_t* B, int nb, int a, int b, int steps, uint64_t* dst) {
-    uint64_t ka = A[a], kb = B[b];
+    const uint64_t* pa = A + a;
+    const uint64_t* pb = B + b;
+    const uint64_t* const ea = A + na;
+    const uint64_t* const eb = B + nb;
+    uint64_t ka = *pa, kb = *pb;
+    if (steps == VT) {  // every thread but the last of a pair
 #pragma unroll
-    for (int it = 0; it < VT; ++it) {
-        if (it < steps) {
-            const bool takeA = (a < na) && (b >= nb || ka <= kb);
+        for (int it = 0; it < VT; ++it) {
+            const bool takeA = (pa < ea) && (pb >= eb || ka <= kb);
             dst[it] = takeA ? ka : kb;
-            if (takeA) ka = A[++a];
-            else kb = B[++b];
+            if (takeA) ka = *++pa;
+            else kb = *++pb;
+        }
+    } else {
+        for (int it = 0; it < steps; ++it) {
+            const bool takeA = (pa < ea) && (pb >= eb || ka <= kb);
+            dst[it] = takeA ? ka : kb;
+            if (takeA) ka = *++pa;
+            else kb = *++pb;
         }
     }
 }
@@ -253,20 +264,38 @@ NW_HD unsigned nw_walk_unique(const uint64_t* A, int na, const uint64_t* B, int 
     uint64_t prev = 0;
     if (a > 0) prev = A[a - 1];
     if (b > 0 && B[b - 1] > prev) prev = B[b - 1];
-    uint64_t ka = A[a], kb = B[b];
+    const uint64_t* pa = A + a;
+    const uint64_t* pb = B + b;
+    const uint64_t* const ea = A + na;
+    const uint64_t* const eb = B + nb;
+    uint64_t ka = *pa, kb = *pb;
     unsigned mask = 0;
+    if (steps == VT) {
 #pragma unroll
-    for (int it = 0; it < VT; ++it) {
-        const bool takeA = (a < na) && (b >= nb || ka <= kb);
-        const uint64_t k = takeA ? ka : kb;
-        outk[it] = k;
-        const bool emit = (it < steps) && (!has_prev || k != prev);
-        mask |= (emit ? 1u : 0u) << it;
-        prev = k;
-        has_prev = true;
-        if (it < steps) {
-            if (takeA) ka = A[++a];
-            else kb = B[++b];
+        for (int it = 0; it < VT; ++it) {
+            const bool takeA = (pa < ea) && (pb >= eb || ka <= kb);
+            const uint64_t k = takeA ? ka : kb;
+            outk[it] = k;
+            mask |= ((!has_prev || k != prev) ? 1u : 0u) << it;
+            prev = k;
+            has_prev = true;
+            if (takeA) ka = *++pa;
+            else kb = *++pb;
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < VT; ++it) {
+            const bool takeA = (pa < ea) && (pb >= eb || ka <= kb);
+            const uint64_t k = takeA ? ka : kb;
+            outk[it] = k;
+            const bool emit = (it < steps) && (!has_prev || k != prev);
+            mask |= (emit ? 1u : 0u) << it;
+            prev = k;
+            has_prev = true;
+            if (it < steps) {
+                if (takeA) ka = *++pa;
+                else kb = *++pb;
+            }
         }
     }
     return mask;
