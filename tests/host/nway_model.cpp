@@ -56,29 +56,33 @@ bool run_union(const std::vector<std::vector<uint64_t>>& files, std::vector<uint
     if (total == 0) return true;
     const long long tile = SH::TILE, tol = SH::TILE / 32;
     const int num_tiles = (int)((total + tile - 1) / tile);
-    const int nc = (num_tiles + NW_COARSE - 1) / NW_COARSE;
-    // ---- coarse + fine partition (nway_coarse_kernel / nway_fine_kernel) ----
-    std::vector<NwBound> coarse(nc + 1);
-    NwBound glo, ghi;
-    nw_global_bracket(F, &glo, &ghi);
-    for (int c = 0; c <= nc; ++c) {
-        const long long R = (long long)c * NW_COARSE * tile;
-        if (c == 0) coarse[c] = glo;
-        else if (c == nc || R >= total) coarse[c] = ghi;
-        else nw_refine(F, R, tol, glo, ghi, &coarse[c]);
+    // ---- three-level partition (nway_partition_kernel: strides 64, 8, 1) ----
+    std::vector<NwBound> bounds(num_tiles + 1);
+    {
+        NwBound glo, ghi;
+        nw_global_bracket(F, &glo, &ghi);
+        bounds[num_tiles] = ghi;
+        const int strides[3] = {64, 8, 1};
+        int parent = 0;
+        for (int L = 0; L < 3; ++L) {
+            const int st = strides[L];
+            for (long long t = 0; t < num_tiles; t += st) {
+                if (parent == 0) {
+                    if (t == 0) bounds[t] = glo;
+                    else nw_refine(F, t * tile, tol, glo, ghi, &bounds[t]);
+                } else {
+                    if (t % parent == 0) continue;
+                    const long long pl = t / parent * parent;
+                    const long long ph = pl + parent < num_tiles ? pl + parent : num_tiles;
+                    nw_refine(F, t * tile, tol, bounds[pl], bounds[ph], &bounds[t]);
+                }
+            }
+            parent = st;
+        }
     }
     std::vector<long long> part((size_t)(num_tiles + 1) * NW_MAX);
-    for (int t = 0; t <= num_tiles; ++t) {
-        NwBound o;
-        if (t == num_tiles) {
-            for (int f = 0; f < NW_MAX; ++f) o.pos[f] = f < nf ? F.n[f] : 0;
-        } else {
-            const int c = t / NW_COARSE;
-            if (t % NW_COARSE == 0) o = coarse[c];
-            else nw_refine(F, (long long)t * tile, tol, coarse[c], coarse[c + 1], &o);
-        }
-        for (int f = 0; f < NW_MAX; ++f) part[(size_t)t * NW_MAX + f] = o.pos[f];
-    }
+    for (int t = 0; t <= num_tiles; ++t)
+        for (int f = 0; f < NW_MAX; ++f) part[(size_t)t * NW_MAX + f] = bounds[t].pos[f];
     // ---- nway_check_kernel ----
     *max_tile = 0;
     for (int t = 0; t < num_tiles; ++t) {
@@ -141,7 +145,7 @@ bool run_union(const std::vector<std::vector<uint64_t>>& files, std::vector<uint
                 if (steps > VT) steps = VT;
                 const uint64_t* A = src + pr.srcA;
                 const uint64_t* B = src + pr.srcB;
-                const int a = nw_merge_path(A, pr.lenA, B, pr.lenB, diag);
+                const int a = nw_merge_path_g(A, pr.lenA, B, pr.lenB, diag);
                 nw_walk_plain<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, dst + pr.dst + diag);
             }
             const uint64_t* tmp = src;
@@ -160,7 +164,7 @@ bool run_union(const std::vector<std::vector<uint64_t>>& files, std::vector<uint
             if (diag > tot) diag = tot;
             const uint64_t* A = src + pr.srcA;
             const uint64_t* B = src + pr.srcB;
-            const int a = nw_merge_path(A, pr.lenA, B, pr.lenB, diag);
+            const int a = nw_merge_path_g(A, pr.lenA, B, pr.lenB, diag);
             uint64_t outk[VT];
             const unsigned mask = nw_walk_unique<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, outk);
             for (int it = 0; it < VT; ++it)
@@ -298,6 +302,8 @@ int main() {
     battery<8, 256, 9>(8);
     battery<8, 128, 17>(7);
     battery<8, 256, 13>(8);
+    battery<8, 512, 13>(8);
+    battery<4, 512, 13>(4);
     battery<4, 256, 9>(4);
     battery<4, 128, 17>(3);
     battery<2, 256, 9>(2);

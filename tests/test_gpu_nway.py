@@ -22,7 +22,7 @@ def exp_union(files):
     return np.unique(np.concatenate([np.asarray(f, dtype=U64) for f in files]))
 
 
-@pytest.mark.parametrize("cfg", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("cfg", ["0", "1", "2", "3", "4"])
 @pytest.mark.parametrize("nf", [2, 3, 4, 5, 7, 8])
 def test_nway_union_shapes(eng, cfg, nf, monkeypatch):
     monkeypatch.setenv("UKM_NWAY_CFG", cfg)

@@ -29,7 +29,7 @@ def timed(stream, fn, reps=3, warm=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--universe", type=float, default=1e9)
-    ap.add_argument("--cfgs", default="off,0,1,2,3")
+    ap.add_argument("--cfgs", default="off,0,1,2,3,4")
     ap.add_argument("--h2d", action="store_true")
     args = ap.parse_args()
     U = int(args.universe)

@@ -24,7 +24,8 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------------
-// partition kernels: one thread per boundary
+// partition kernels: one thread per boundary, three levels (every 64th tile from the global bracket, every
+// 8th from those, every tile from those) so that the bracket of a search is always small
 // ---------------------------------------------------------------------------------------------------
 struct NwPartArgs {
     NwFiles F;
@@ -32,47 +33,41 @@ struct NwPartArgs {
     long long tile;  // nominal elements per tile
     long long tol;   // accepted rank error of a boundary
     int num_tiles;
-    int nc;          // coarse chunks
 };
 
-__global__ void nway_coarse_kernel(const NwPartArgs a, NwBound* __restrict__ coarse) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > a.nc) return;
-    NwBound lo, hi, out;
-    nw_global_bracket(a.F, &lo, &hi);
-    const long long R = (long long)c * NW_COARSE * a.tile;
-    if (c == 0) out = lo;
-    else if (c == a.nc || R >= a.total) out = hi;
-    else nw_refine(a.F, R, a.tol, lo, hi, &out);
-    coarse[c] = out;
-}
-
-// part[t * NW_MAX + f] = first element of tile t in file f; row num_tiles = the file lengths
-__global__ void nway_fine_kernel(const NwPartArgs a, const NwBound* __restrict__ coarse, long long* __restrict__ part) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > a.num_tiles) return;
-    NwBound out;
-    if (t == a.num_tiles) {
-#pragma unroll
-        for (int f = 0; f < NW_MAX; ++f) out.pos[f] = (f < a.F.nf) ? a.F.n[f] : 0;
-    } else {
-        const int c = t / NW_COARSE;
-        if (t % NW_COARSE == 0) out = coarse[c];
-        else nw_refine(a.F, (long long)t * a.tile, a.tol, coarse[c], coarse[c + 1], &out);
+// bounds[t] = the cut in front of tile t (t = num_tiles: the end of every file).  One launch per level:
+// boundaries at multiples of `stride` that the level above (multiples of `parent`; 0 = none) has not produced.
+__global__ void nway_partition_kernel(const NwPartArgs a, NwBound* __restrict__ bounds, int stride, int parent) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t = i * stride;
+    if (t > a.num_tiles && !(parent == 0 && i == 0)) return;
+    if (parent == 0) {
+        NwBound lo, hi, out;
+        nw_global_bracket(a.F, &lo, &hi);
+        if (i == 0) bounds[a.num_tiles] = hi;  // the end boundary
+        if (t >= a.num_tiles) return;
+        if (t == 0) out = lo;
+        else nw_refine(a.F, t * a.tile, a.tol, lo, hi, &out);
+        bounds[t] = out;
+        return;
     }
-#pragma unroll
-    for (int f = 0; f < NW_MAX; ++f) part[(size_t)t * NW_MAX + f] = out.pos[f];
+    if (t >= a.num_tiles || t % parent == 0) return;
+    const long long pl = t / parent * parent;
+    const long long ph = pl + parent < a.num_tiles ? pl + parent : a.num_tiles;
+    NwBound out;
+    nw_refine(a.F, t * a.tile, a.tol, bounds[pl], bounds[ph], &out);
+    bounds[t] = out;
 }
 
 // every tile must fit the shared-memory slot (it does for duplicate-free inputs); info[0] = bad flag, info[1] = largest tile
-__global__ void nway_check_kernel(const long long* __restrict__ part, int num_tiles, int cap, int* __restrict__ info) {
+__global__ void nway_check_kernel(const NwBound* __restrict__ bounds, int num_tiles, int cap, int* __restrict__ info) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= num_tiles) return;
     long long sum = 0;
     bool bad = false;
 #pragma unroll
     for (int f = 0; f < NW_MAX; ++f) {
-        const long long d = part[(size_t)(t + 1) * NW_MAX + f] - part[(size_t)t * NW_MAX + f];
+        const long long d = bounds[t + 1].pos[f] - bounds[t].pos[f];
         if (d < 0) bad = true;
         sum += d;
     }
@@ -90,7 +85,7 @@ constexpr int NWK_AUX = 64;        // loader + prefix warps
 
 struct NwArgs {
     NwFiles F;
-    const long long* part;
+    const NwBound* bounds;  // bounds[t].pos[f] = first element of tile t in file f
     uint64_t* outK;
     uint64_t* status;  // one count word per tile (flag << 62 | count)
     unsigned long long* total_out;
@@ -155,8 +150,8 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_union_kernel(const Nw
             long long lo = 0;
             int n = 0;
             if (lane < NWAY) {
-                lo = p.part[(size_t)tile * NW_MAX + lane];
-                const long long hi = p.part[(size_t)(tile + 1) * NW_MAX + lane];
+                lo = p.bounds[tile].pos[lane];
+                const long long hi = p.bounds[tile + 1].pos[lane];
                 n = (int)(hi - lo);
             }
             int sum = n;
@@ -291,7 +286,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_union_kernel(const Nw
                     if (steps > VT) steps = VT;
                     const uint64_t* A = src + pr.srcA;
                     const uint64_t* B = src + pr.srcB;
-                    const int a = nw_merge_path(A, pr.lenA, B, pr.lenB, diag);
+                    const int a = nw_merge_path_g(A, pr.lenA, B, pr.lenB, diag);
                     nw_walk_plain<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, dst + pr.dst + diag);
                 }
                 named_bar_sync(1, NT);
@@ -310,7 +305,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_union_kernel(const Nw
                 if (diag > tot) diag = tot;
                 const uint64_t* A = src + pr.srcA;
                 const uint64_t* B = src + pr.srcB;
-                const int a = nw_merge_path(A, pr.lenA, B, pr.lenB, diag);
+                const int a = nw_merge_path_g(A, pr.lenA, B, pr.lenB, diag);
                 emitmask = nw_walk_unique<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, outk);
             }
             unsigned tile_total;
@@ -368,22 +363,25 @@ int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_
     pa.tol = SH::TILE / 32;
     const int num_tiles = (int)((pa.total + SH::TILE - 1) / SH::TILE);
     pa.num_tiles = num_tiles;
-    pa.nc = (num_tiles + NW_COARSE - 1) / NW_COARSE;
-    NwBound* d_coarse = nullptr;
-    long long* d_part = nullptr;
+    NwBound* d_bounds = nullptr;
     uint64_t* d_status = nullptr;
-    UKM_TRY(tmp.alloc(&d_coarse, (size_t)pa.nc + 1));
-    UKM_TRY(tmp.alloc(&d_part, (size_t)(num_tiles + 1) * NW_MAX));
+    UKM_TRY(tmp.alloc(&d_bounds, (size_t)num_tiles + 1));
     UKM_TRY(tmp.alloc(&d_status, (size_t)num_tiles + 4));
     // output total and the check words live in the tail of the status allocation (zeroed together)
     unsigned long long* d_total = reinterpret_cast<unsigned long long*>(d_status + num_tiles);
     int* d_info = reinterpret_cast<int*>(d_status + num_tiles + 1);
     UKM_CUDA(ctx, cudaMemsetAsync(d_status, 0, ((size_t)num_tiles + 4) * sizeof(uint64_t), ctx->stream));
-    nway_coarse_kernel<<<(pa.nc + 1 + 63) / 64, 64, 0, ctx->stream>>>(pa, d_coarse);
-    UKM_LAUNCHED(ctx);
-    nway_fine_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(pa, d_coarse, d_part);
-    UKM_LAUNCHED(ctx);
-    nway_check_kernel<<<(num_tiles + 127) / 128, 128, 0, ctx->stream>>>(d_part, num_tiles, SH::CAP, d_info);
+    {
+        constexpr int S0 = 64, S1 = 8;
+        const int n0 = num_tiles / S0 + 1, n1 = num_tiles / S1 + 1;
+        nway_partition_kernel<<<(n0 + 63) / 64, 64, 0, ctx->stream>>>(pa, d_bounds, S0, 0);
+        UKM_LAUNCHED(ctx);
+        nway_partition_kernel<<<(n1 + 63) / 64, 64, 0, ctx->stream>>>(pa, d_bounds, S1, S0);
+        UKM_LAUNCHED(ctx);
+        nway_partition_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(pa, d_bounds, 1, S1);
+        UKM_LAUNCHED(ctx);
+    }
+    nway_check_kernel<<<(num_tiles + 127) / 128, 128, 0, ctx->stream>>>(d_bounds, num_tiles, SH::CAP, d_info);
     UKM_LAUNCHED(ctx);
     UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_info, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -391,7 +389,7 @@ int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_
         *fell_back = true;  // some key occurs far too often for a tile: inputs are not duplicate-free
         return UKM_OK;
     }
-    a.part = d_part;
+    a.bounds = d_bounds;
     a.status = d_status;
     a.total_out = d_total;
     a.num_tiles = num_tiles;
@@ -402,8 +400,7 @@ int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_
     UKM_LAUNCHED(ctx);
     UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    tmp.free_now(d_coarse);
-    tmp.free_now(d_part);
+    tmp.free_now(d_bounds);
     tmp.free_now(d_status);
     return UKM_OK;
 }
@@ -412,16 +409,17 @@ int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_
 int nway_cfg() {
     const char* e = getenv("UKM_NWAY_CFG");
     const int v = e ? atoi(e) : 0;
-    return (v >= 0 && v < 4) ? v : 0;
+    return (v >= 0 && v < 5) ? v : 0;
 }
 
 template <int NWAY>
 int launch_nway_cfg(ukm_ctx* ctx, const NwArgs& a, const NwPartArgs& pa, ukm_tmp& tmp, bool* fell_back) {
     switch (nway_cfg()) {
         case 1: return launch_nway<NWAY, 128, 17, 3, 3>(ctx, a, pa, tmp, fell_back);
-        case 2: return launch_nway<NWAY, 256, 13, 3, 2>(ctx, a, pa, tmp, fell_back);
+        case 2: return launch_nway<NWAY, 512, 13, 3, 1>(ctx, a, pa, tmp, fell_back);
         case 3: return launch_nway<NWAY, 128, 17, 4, 2>(ctx, a, pa, tmp, fell_back);
-        default: return launch_nway<NWAY, 256, 9, 3, 3>(ctx, a, pa, tmp, fell_back);
+        case 4: return launch_nway<NWAY, 256, 9, 3, 3>(ctx, a, pa, tmp, fell_back);
+        default: return launch_nway<NWAY, 256, 13, 3, 2>(ctx, a, pa, tmp, fell_back);
     }
 }
 
