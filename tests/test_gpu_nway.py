@@ -112,3 +112,86 @@ def test_nway_union_falls_back_on_inputs_that_cannot_be_tiled(eng, monkeypatch):
     if got is not None:
         same(got, old, "fallback result = two-way tree result")
         assert np.array_equal(np.unique(got), exp_union(files))
+
+
+# ---------------------------------------------------------------------------------------
+# N-way inter / diff (hash filter per tile; replaces inter.go:205-267 / diff.go:380-435 file by file)
+# ---------------------------------------------------------------------------------------
+def exp_inter(files):
+    r = np.asarray(files[0], dtype=U64)
+    for f in files[1:]:
+        r = r[np.isin(r, f)]
+    return r
+
+
+def exp_diff(files):
+    r = np.asarray(files[0], dtype=U64)
+    for f in files[1:]:
+        r = r[~np.isin(r, f)]
+    return r
+
+
+@pytest.mark.parametrize("cfg", ["0", "1", "2", "3", "4"])
+@pytest.mark.parametrize("nf", [3, 4, 5, 8])
+def test_nway_filter_shapes(eng, cfg, nf, monkeypatch):
+    monkeypatch.setenv("UKM_NWAY_CFG", cfg)
+    monkeypatch.setenv("UKM_NWAY_FORCE", "1")
+    for N in (3_000, 250_000, 2_500_000):
+        files = member_files(N, nf)
+        same(eng.inter(files)[0], oracle.inter(files)[0], f"inter cfg {cfg} nf {nf} N {N}")
+        same(eng.diff(files)[0], oracle.diff(files)[0], f"diff cfg {cfg} nf {nf} N {N}")
+
+
+@pytest.mark.parametrize("nf", [9, 15, 16, 20])
+def test_nway_filter_more_than_eight_files(eng, nf, monkeypatch):
+    monkeypatch.setenv("UKM_NWAY_FORCE", "1")
+    r = rng(nf)
+    uni = np.unique(r.integers(0, 2**62, 300_000, dtype=U64))
+    files = [uni[r.random(len(uni)) < 0.9] for _ in range(nf)]
+    same(eng.inter(files)[0], exp_inter(files), f"inter of {nf} files")
+    files = [uni[r.random(len(uni)) < 0.5]] + [uni[r.random(len(uni)) < 0.1] for _ in range(nf - 1)]
+    same(eng.diff(files)[0], exp_diff(files), f"diff of {nf} files")
+
+
+def test_nway_filter_matches_file_by_file(eng, monkeypatch):
+    files = member_files(1_000_000, 8)
+    a_i, a_d = eng.inter(files)[0], eng.diff(files)[0]
+    monkeypatch.setenv("UKM_NWAY", "0")
+    same(a_i, eng.inter(files)[0], "inter: nway vs file by file")
+    same(a_d, eng.diff(files)[0], "diff: nway vs file by file")
+
+
+def test_nway_filter_distributions(eng, monkeypatch):
+    monkeypatch.setenv("UKM_NWAY_FORCE", "1")
+    r = rng(21)
+    cases = {}
+    base = np.unique(r.integers(0, 2**64, 300_000, dtype=U64))
+    fs = [base[r.random(len(base)) < 0.7] for _ in range(8)]
+    for q in (0, 3, 7):
+        fs[q] = np.unique(np.concatenate([fs[q], np.array([0, 2**64 - 1], dtype=U64)]))
+    cases["extremes"] = fs
+    cases["identical"] = [base.copy() for _ in range(5)]
+    # file 0 dominates some tiles (dense runs of consecutive integers): the binary-search path of a tile
+    big0 = np.unique(np.concatenate([r.integers(0, 2**63, 20_000, dtype=U64), U64(10**12) + np.arange(300_000, dtype=U64)]))
+    cases["file0_dense"] = [big0] + [np.unique(np.concatenate([r.integers(0, 2**63, 20_000, dtype=U64),
+                                                               U64(10**12) + np.arange(0, 300_000, 3 + q, dtype=U64)])) for q in range(4)]
+    # one tile holding key 0 and key 2^64-1 of file 0: no value left for "empty"
+    cases["tiny_extremes"] = [np.array([0, 5, 9, 2**64 - 1], dtype=U64), np.array([0, 9, 2**64 - 1], dtype=U64),
+                              np.array([5, 9, 2**64 - 1], dtype=U64)]
+    cases["disjoint"] = [np.unique(r.integers(q << 50, (q << 50) + 2**30, 5000 << (q % 5), dtype=U64)) for q in range(6)]
+    cases["geometric"] = [np.unique(np.exp2(r.random(150_000) * 40 + 20).astype(U64)) for _ in range(8)]
+    cases["small_first"] = [base[::50].copy()] + [base[r.random(len(base)) < 0.8] for _ in range(4)]
+    cases["with_empty_subject"] = [base[::2].copy(), base[::3].copy(), np.zeros(0, dtype=U64), base[::5].copy(), base[::7].copy()]
+    for name, files in cases.items():
+        same(eng.inter(files)[0], oracle.inter(files)[0], f"inter {name}")
+        same(eng.diff(files)[0], oracle.diff(files)[0], f"diff {name}")
+
+
+def test_nway_filter_misaligned_device_pointers(eng, monkeypatch):
+    import torch
+    monkeypatch.setenv("UKM_NWAY_FORCE", "1")
+    files = member_files(700_000, 6)
+    d = [torch.from_numpy(f.view(np.int64)).cuda()[(i % 2):] for i, f in enumerate(files)]
+    h = [x.cpu().numpy().view(U64) for x in d]
+    same(eng.inter(d)[0].cpu().numpy().view(U64), exp_inter(h), "misaligned inter")
+    same(eng.diff(d)[0].cpu().numpy().view(U64), exp_diff(h), "misaligned diff")

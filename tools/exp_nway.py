@@ -63,6 +63,33 @@ def main():
                               "algo_GBps": (total + n_out) * 8 / ms / 1e6, "n_out": n_out, "same_as_first": (n_out, chk) == ref,
                               "kernels": {k: {"launches": v["launches"], "ms_per_launch": round(v["ms"] / max(v["launches"], 1), 3)}
                                           for k, v in st.items()}}), flush=True)
+        # inter / diff: N-way hash filter against the file-by-file passes
+        oi = torch.empty(int(files[0].shape[0]) + 16, dtype=torch.int64, device="cuda")
+        for name, fn in (("inter8", eng.inter), ("diff8", eng.diff)):
+            ref = None
+            for cfg in args.cfgs.split(","):
+                if cfg == "off":
+                    os.environ["UKM_NWAY"] = "0"
+                else:
+                    os.environ["UKM_NWAY"] = "1"
+                    os.environ["UKM_NWAY_CFG"] = cfg
+                res = {}
+
+                def run():
+                    res["r"] = fn(files, out=oi)[0]
+                eng.stats_reset(); eng.stats_enable(True)
+                ms = timed(stream, run)
+                eng.stats_enable(False)
+                st = eng.stats()
+                n_out = int(res["r"].shape[0])
+                chk = int(res["r"].sum().item())
+                if ref is None:
+                    ref = (n_out, chk)
+                print(json.dumps({"bench": name, "cfg": cfg, "ms": ms, "kmers_in_per_s": total / ms * 1e3,
+                                  "algo_GBps": (total + n_out) * 8 / ms / 1e6, "n_out": n_out, "same_as_first": (n_out, chk) == ref,
+                                  "kernels": {k: {"launches": v["launches"], "ms_per_launch": round(v["ms"] / max(v["launches"], 1), 3)}
+                                              for k, v in st.items()}}), flush=True)
+        os.environ["UKM_NWAY"] = "1"
         for sub in (2, 4):
             os.environ["UKM_NWAY"] = "1"
             os.environ["UKM_NWAY_CFG"] = "0"

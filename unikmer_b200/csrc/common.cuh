@@ -143,6 +143,8 @@ int ukm_dev_check_sorted_unique(ukm_ctx* ctx, const uint64_t* d_keys, size_t n);
 bool ukm_nway_enabled();
 int ukm_nway_union(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
                    bool* fell_back);
+int ukm_nway_filter(ukm_ctx* ctx, bool inter, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
+                    bool* fell_back);
 
 static inline int ukm_grid_for(size_t work, int per_block, int sm_count, int max_per_sm = 32) {
     size_t g = (work + per_block - 1) / per_block;

@@ -83,6 +83,8 @@ __global__ void nway_check_kernel(const NwBound* __restrict__ bounds, int num_ti
 constexpr int NWK_MAX_GRID = 512;  // prefix warp keeps NWK_MAX_GRID/32 counts per lane
 constexpr int NWK_AUX = 64;        // loader + prefix warps
 
+enum NwOp { NWOP_UNION = 0, NWOP_INTER = 1, NWOP_DIFF = 2 };
+
 struct NwArgs {
     NwFiles F;
     const NwBound* bounds;  // bounds[t].pos[f] = first element of tile t in file f
@@ -108,15 +110,130 @@ struct NwShape {
     static constexpr int LEVELS = NwGeom<NWAY>::LEVELS;
 };
 
-template <int NWAY, int NT, int VT, int SLOTS, int MINB>
-__global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_union_kernel(const NwArgs p) {
+// ---- inter / diff of one tile: which of file 0's keys occur in the other files -----------------------------
+// The tile's file-0 keys go into an open-addressing table in shared memory (64-bit keys, linear probing, at most
+// half full); every key of every other file is looked up once and, on a hit, sets its file's bit in the byte that
+// belongs to the table slot.  A file-0 key survives `inter` when all bits are set, `diff` when none is.  That is
+// inter.go:205-267 / diff.go:380-435 for all files at once: a two-pointer walk per file costs a shared-memory
+// load per element per file, this costs about one probe per element.  Tiles whose file-0 share does not fit the
+// table (or that hold both key 0 and key 2^64-1, leaving no value for "empty") mark hits by binary search instead.
+constexpr int NWF_TABN = 2048;  // table slots
+constexpr int NWF_EPT = 4;      // file-0 keys per thread on the table path
+
+__device__ __forceinline__ unsigned nwf_hash(uint64_t x) {
+    return (unsigned)((x * 0x9E3779B97F4A7C15ull) >> 53);  // top 11 bits of the Fibonacci product: [0, 2048)
+}
+
+template <int OP, int NT, int VT>
+__device__ __forceinline__ unsigned nw_filter_tile(const uint64_t* slot, const NwGeom<NW_MAX>& g, uint64_t* tab, uint32_t* m32,
+                                                   int tid, int nf, uint64_t* outk) {
+    constexpr int CAP = NwShape<NW_MAX, NT, VT>::CAP;
+    constexpr int MW = ((CAP > NWF_TABN ? CAP : NWF_TABN) + 3) / 4;  // one byte per table slot / per file-0 position
+    const unsigned lane = lane_id();
+    const int n0 = g.n[0];
+    const uint64_t* seg0 = slot + g.off[0];
+    const int ept = (n0 + NT - 1) / NT;  // file-0 keys per thread, blocked: thread t owns [t*ept, (t+1)*ept)
+    const uint64_t lo0 = n0 ? seg0[0] : 1, hi0 = n0 ? seg0[n0 - 1] : 1;
+    const uint64_t EMPTY = lo0 > 0 ? lo0 - 1 : hi0 + 1;  // a value no file-0 key of this tile has
+    const bool hashed = (lo0 > 0 || hi0 != ~0ull) && n0 <= NWF_TABN / 2 && ept <= NWF_EPT;
+    // A: clear
+    if (hashed)
+        for (int j = tid; j < NWF_TABN; j += NT) tab[j] = EMPTY;
+    for (int j = tid; j < MW; j += NT) m32[j] = 0;
+    named_bar_sync(1, NT);
+    // B: my file-0 keys (kept in registers; on the table path also inserted)
+    int hs[NWF_EPT];
+#pragma unroll
+    for (int r = 0; r < NWF_EPT; ++r) hs[r] = 0;
+#pragma unroll
+    for (int r = 0; r < VT; ++r) {
+        const int i0 = tid * ept + r;
+        outk[r] = 0;
+        if (r < ept && i0 < n0) {
+            const uint64_t x = seg0[i0];
+            outk[r] = x;
+            if (r < NWF_EPT && hashed) {
+                unsigned h = nwf_hash(x);
+                for (int pr = 0; pr < NWF_TABN; ++pr) {
+                    const unsigned long long old =
+                        atomicCAS(reinterpret_cast<unsigned long long*>(&tab[h]), (unsigned long long)EMPTY, (unsigned long long)x);
+                    if (old == EMPTY || old == x) break;
+                    h = (h + 1) & (NWF_TABN - 1);
+                }
+                hs[r] = (int)h;
+            }
+        }
+    }
+    named_bar_sync(1, NT);
+    // C: every key of files 1..nf-1, in chunks of 32 handed to the warps round robin
+    {
+        const int nfl = (lane >= 1 && (int)lane < nf) ? g.n[lane] : 0;
+        const int ch = (nfl + 31) >> 5;
+        const int incl = (int)warp_incl_scan_u32((unsigned)ch);
+        const int total_ch = __shfl_sync(0xffffffffu, incl, 31);
+        for (int c = tid >> 5; c < total_ch; c += NT / 32) {
+            const int f = __popc(__ballot_sync(0xffffffffu, incl <= c));  // first file whose chunks reach past c
+            const int excl_f = __shfl_sync(0xffffffffu, incl - ch, f);
+            const int n_f = __shfl_sync(0xffffffffu, nfl, f);
+            const int i = (c - excl_f) * 32 + (int)lane;
+            if (i < n_f) {
+                const uint64_t y = slot[g.off[f] + i];
+                int hit = -1;
+                if (hashed) {
+                    unsigned h = nwf_hash(y);
+                    for (int pr = 0; pr < NWF_TABN; ++pr) {
+                        const uint64_t k = tab[h];
+                        if (k == EMPTY) break;
+                        if (k == y) { hit = (int)h; break; }
+                        h = (h + 1) & (NWF_TABN - 1);
+                    }
+                } else {
+                    int pos = 0, n = n0;  // lower_bound of y in file 0's keys; the answer lies in [pos, pos + n]
+                    while (n > 1) {
+                        const int half = n >> 1;
+                        if (seg0[pos + half] < y) pos += half;
+                        n -= half;
+                    }
+                    if (n == 1 && seg0[pos] < y) ++pos;
+                    if (pos < n0 && seg0[pos] == y) hit = pos;
+                }
+                if (hit >= 0) atomicOr(&m32[hit >> 2], (1u << f) << ((hit & 3) * 8));
+            }
+        }
+    }
+    named_bar_sync(1, NT);
+    // D: verdict per file-0 key
+    const unsigned full = ((1u << nf) - 1u) & ~1u;
+    unsigned mask = 0;
+#pragma unroll
+    for (int r = 0; r < VT; ++r) {
+        const int i0 = tid * ept + r;
+        if (r < ept && i0 < n0) {
+            const int idx = (hashed && r < NWF_EPT) ? hs[r < NWF_EPT ? r : 0] : i0;
+            const unsigned m = (m32[idx >> 2] >> ((idx & 3) * 8)) & 0xffu;
+            const bool keep = OP == NWOP_INTER ? (m == full) : (m == 0);
+            mask |= (keep ? 1u : 0u) << r;
+        }
+    }
+    return mask;
+}
+
+template <int OP, int NWAY, int NT, int VT>
+constexpr int nw_x_elems() {  // the second shared-memory region: merge buffer X (union) or table + hit bytes (inter / diff)
     using SH = NwShape<NWAY, NT, VT>;
+    return OP == NWOP_UNION ? SH::X_E : NWF_TABN + (((SH::CAP > NWF_TABN ? SH::CAP : NWF_TABN) + 3) / 4 + 1) / 2 + 2;
+}
+
+template <int OP, int NWAY, int NT, int VT, int SLOTS, int MINB>
+__global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p) {
+    using SH = NwShape<NWAY, NT, VT>;
+    static_assert(OP == NWOP_UNION || NWAY == NW_MAX, "inter / diff tiles are laid out for 8 files");
     constexpr int NW = NT / 32;
     constexpr int DEFER = SLOTS - 2;
     constexpr int LEVELS = SH::LEVELS;
     extern __shared__ __align__(16) unsigned char nw_smem[];
     uint64_t* s_slots = reinterpret_cast<uint64_t*>(nw_smem);  // SLOTS * SLOT_E
-    uint64_t* s_x = s_slots + (size_t)SLOTS * SH::SLOT_E;      // X_E
+    uint64_t* s_x = s_slots + (size_t)SLOTS * SH::SLOT_E;      // nw_x_elems()
     __shared__ __align__(8) uint64_t full_bar[SLOTS], empty_bar[SLOTS], pre_bar[SLOTS];
     __shared__ unsigned long long s_cnt[SLOTS], s_pre[SLOTS];
     __shared__ NwGeom<NWAY> s_geom[SLOTS];
@@ -189,7 +306,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_union_kernel(const Nw
             }
             __syncwarp();
             if (lane == 0) {
-                nw_build_tables<NWAY, VT>(&s_geom[s]);
+                if (OP == NWOP_UNION) nw_build_tables<NWAY, VT>(&s_geom[s]);
                 mbar_expect_tx(&full_bar[s], bytes);  // arrive (release: publishes the plain stores and the tables) + tx count
             }
             __syncwarp();
@@ -267,6 +384,9 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_union_kernel(const Nw
                 if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
             }
             const NwGeom<NWAY>& g = s_geom[s];
+            if constexpr (OP != NWOP_UNION) {
+                emitmask = nw_filter_tile<OP, NT, VT>(slot, g, s_x, reinterpret_cast<uint32_t*>(s_x + NWF_TABN), tid, p.F.nf, outk);
+            } else {
             const uint64_t* src = slot;
             uint64_t* dst = s_x;
             // inner levels: plain two-way merges, every pair of runs by its own group of threads
@@ -308,6 +428,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_union_kernel(const Nw
                 const int a = nw_merge_path_g(A, pr.lenA, B, pr.lenB, diag);
                 emitmask = nw_walk_unique<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, outk);
             }
+            }  // union
             unsigned tile_total;
             off = group_excl_scan_u32<NT>((unsigned)__popc(emitmask), (unsigned)tid, s_scan, &tile_total, 1);
             // every consumer is past its reads of the slot (two barriers inside the scan): it may be overwritten
@@ -345,17 +466,17 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_union_kernel(const Nw
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-template <int NWAY, int NT, int VT, int SLOTS, int MINB>
+template <int OP, int NWAY, int NT, int VT, int SLOTS, int MINB>
 int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_back) {
     using SH = NwShape<NWAY, NT, VT>;
-    constexpr size_t smem = ((size_t)SLOTS * SH::SLOT_E + SH::X_E) * 8;
-    auto kern = nway_union_kernel<NWAY, NT, VT, SLOTS, MINB>;
+    constexpr size_t smem = ((size_t)SLOTS * SH::SLOT_E + nw_x_elems<OP, NWAY, NT, VT>()) * 8;
+    auto kern = nway_kernel<OP, NWAY, NT, VT, SLOTS, MINB>;
     static int ctas_per_sm = 0;  // per instantiation
     if (ctas_per_sm == 0) {
         UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
         UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT + NWK_AUX, smem));
-        if (nb < 1) return ukm_fail(ctx, UKM_E_INTERNAL, "nway_union_kernel does not fit on an SM");
+        if (nb < 1) return ukm_fail(ctx, UKM_E_INTERNAL, "nway_kernel does not fit on an SM");
         ctas_per_sm = nb;
     }
     // ---- partition: tiles of ~TILE elements summed over all files ----
@@ -412,32 +533,22 @@ int nway_cfg() {
     return (v >= 0 && v < 5) ? v : 0;
 }
 
-template <int NWAY>
+template <int OP, int NWAY>
 int launch_nway_cfg(ukm_ctx* ctx, const NwArgs& a, const NwPartArgs& pa, ukm_tmp& tmp, bool* fell_back) {
     switch (nway_cfg()) {
-        case 1: return launch_nway<NWAY, 128, 17, 3, 3>(ctx, a, pa, tmp, fell_back);
-        case 2: return launch_nway<NWAY, 512, 13, 3, 1>(ctx, a, pa, tmp, fell_back);
-        case 3: return launch_nway<NWAY, 128, 17, 4, 2>(ctx, a, pa, tmp, fell_back);
-        case 4: return launch_nway<NWAY, 256, 9, 3, 3>(ctx, a, pa, tmp, fell_back);
-        default: return launch_nway<NWAY, 256, 13, 3, 2>(ctx, a, pa, tmp, fell_back);
+        case 1: return launch_nway<OP, NWAY, 128, 17, 3, 3>(ctx, a, pa, tmp, fell_back);
+        case 2: return launch_nway<OP, NWAY, 512, 13, 3, 1>(ctx, a, pa, tmp, fell_back);
+        case 3: return launch_nway<OP, NWAY, 128, 17, 4, 2>(ctx, a, pa, tmp, fell_back);
+        case 4: return launch_nway<OP, NWAY, 256, 9, 3, 3>(ctx, a, pa, tmp, fell_back);
+        default: return launch_nway<OP, NWAY, 256, 13, 3, 2>(ctx, a, pa, tmp, fell_back);
     }
 }
 
-}  // namespace
-
-bool ukm_nway_enabled() {
-    const char* e = getenv("UKM_NWAY");
-    return !(e && e[0] == '0');
-}
-
-// Union of nf (2..8) sorted duplicate-free device arrays into outK (capacity >= sum of the lengths).
-// *fell_back = true (and nothing written) when the inputs cannot be tiled -- the caller then uses the
-// two-way tree, which takes any input.
-int ukm_nway_union(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
-                   bool* fell_back) {
+int nway_run(ukm_ctx* ctx, int op, const char* stat_name, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK,
+             size_t* n_out, bool* fell_back) {
     *fell_back = false;
     *n_out = 0;
-    if (nf < 2 || nf > NW_MAX) return ukm_fail(ctx, UKM_E_ARG, "ukm_nway_union: 2..8 inputs");
+    if (nf < 2 || nf > NW_MAX) return ukm_fail(ctx, UKM_E_ARG, "nway: 2..8 inputs");
     NwArgs a;
     NwPartArgs pa;
     long long total = 0;
@@ -454,11 +565,13 @@ int ukm_nway_union(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, i
     a.err = ctx->d_err;
     ukm_tmp tmp(ctx);
     {
-        ukm_stat_scope st(ctx, "setop_union_nway", (double)total * 8.0);
+        ukm_stat_scope st(ctx, stat_name, (double)total * 8.0);  // every input key read once (+ the output, added below)
         int r;
-        if (nf <= 2) r = launch_nway_cfg<2>(ctx, a, pa, tmp, fell_back);
-        else if (nf <= 4) r = launch_nway_cfg<4>(ctx, a, pa, tmp, fell_back);
-        else r = launch_nway_cfg<8>(ctx, a, pa, tmp, fell_back);
+        if (op == NWOP_INTER) r = launch_nway_cfg<NWOP_INTER, 8>(ctx, a, pa, tmp, fell_back);
+        else if (op == NWOP_DIFF) r = launch_nway_cfg<NWOP_DIFF, 8>(ctx, a, pa, tmp, fell_back);
+        else if (nf <= 2) r = launch_nway_cfg<NWOP_UNION, 2>(ctx, a, pa, tmp, fell_back);
+        else if (nf <= 4) r = launch_nway_cfg<NWOP_UNION, 4>(ctx, a, pa, tmp, fell_back);
+        else r = launch_nway_cfg<NWOP_UNION, 8>(ctx, a, pa, tmp, fell_back);
         UKM_TRY(r);
     }
     if (*fell_back) {
@@ -468,4 +581,27 @@ int ukm_nway_union(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, i
     *n_out = (size_t)ctx->h_scratch[0];
     if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes += (double)*n_out * 8.0;
     return UKM_OK;
+}
+
+}  // namespace
+
+bool ukm_nway_enabled() {
+    const char* e = getenv("UKM_NWAY");
+    return !(e && e[0] == '0');
+}
+
+// Union of nf (2..8) sorted duplicate-free device arrays into outK (capacity >= sum of the lengths).
+// *fell_back = true (and nothing written) when the inputs cannot be tiled -- the caller then uses the
+// two-way tree, which takes any input.
+int ukm_nway_union(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
+                   bool* fell_back) {
+    return nway_run(ctx, NWOP_UNION, "setop_union_nway", keys, n, nf, outK, n_out, fell_back);
+}
+
+// keys[0] filtered by membership in keys[1..nf-1] (3..8 arrays): inter keeps the keys found in every other array,
+// diff the keys found in none.  outK capacity >= n[0].  Same fall-back contract as the union.
+int ukm_nway_filter(ukm_ctx* ctx, bool inter, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
+                    bool* fell_back) {
+    return nway_run(ctx, inter ? NWOP_INTER : NWOP_DIFF, inter ? "setop_inter_nway" : "setop_diff_nway", keys, n, nf, outK, n_out,
+                    fell_back);
 }

@@ -1080,7 +1080,15 @@ int need_tax(ukm_ctx* ctx, unsigned flags, const char* what) {
     return UKM_OK;
 }
 
-// running op in file order: cur = in[0]; cur = cur OP in[i]   (inter.go / diff.go iteration)
+// UKM_NWAY_FORCE=1: take the N-way filter whenever it applies, whatever the size ratios (tests)
+bool nway_force() {
+    const char* e = getenv("UKM_NWAY_FORCE");
+    return e && e[0] == '1';
+}
+
+// running op in file order: cur = in[0]; cur = cur OP in[i]   (inter.go / diff.go iteration).
+// Keys-only runs of sorted files go through the single-pass N-way filter (nway.cu) up to seven files at a
+// time: the result is the same set the file-by-file iteration produces, every input is read once.
 int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags, ukm_span* out, const char* what) {
     const bool tax = (flags & (UKM_F_TAXID | UKM_F_MIX_TAXID)) != 0;
     ukm_tmp tmp(ctx);
@@ -1092,13 +1100,65 @@ int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags
     const size_t cap = in[0].n;
     DevSet bufs[2];
     int which = 0;
-    for (int i = 1; i < n_in; ++i) {
+    bool nway = !tax && ukm_nway_enabled();
+    int i = 1;
+    while (i < n_in) {
         if (op == OP_INTER) {
             if (cur.n == 0 && cur_is_input) return ukm_fail(ctx, UKM_E_PANIC, "%s: first input is empty (inter.go:208 panics)", what);
             if (in[i].n == 0) break;  // inter.go:211-215: flagBreak keeps the current set (quirk B-3)
         }
-        if (op == OP_DIFF && in[i].n == 0) continue;
+        if (op == OP_DIFF && in[i].n == 0) { ++i; continue; }
         if (cur.n == 0) break;
+        if (nway) {
+            // the files the next N-way pass can take: sorted, non-empty (an empty file ends inter, diff skips it)
+            int idx[NW_FANIN];
+            int g = 0, j = i;
+            size_t total = cur.n, largest = 0;
+            while (j < n_in && g < NW_FANIN - 1) {
+                if (in[j].n == 0) {
+                    if (op == OP_INTER) break;
+                    ++j;
+                    continue;
+                }
+                if (op == OP_DIFF && !in[j].sorted) break;
+                idx[g++] = j++;
+                total += in[idx[g - 1]].n;
+                if (in[idx[g - 1]].n > largest) largest = in[idx[g - 1]].n;
+            }
+            // worth it when file 0's share of a tile fits the hash table and it is not so sparse that looking its
+            // keys up (setop_search_kernel) touches only a fraction of the other files
+            if (g >= 2 && ((cur.n * 3 <= total && cur.n * 64 >= largest) || nway_force())) {
+                DevSet G[NW_FANIN];
+                const uint64_t* ks[NW_FANIN];
+                size_t ns[NW_FANIN];
+                ks[0] = cur.k;
+                ns[0] = cur.n;
+                for (int q = 0; q < g; ++q) {
+                    UKM_TRY(stage_set(ctx, tmp, &in[idx[q]], false, &G[q], &owned, validate));
+                    ks[q + 1] = G[q].k;
+                    ns[q + 1] = G[q].n;
+                }
+                if (bufs[which].k == nullptr) UKM_TRY(alloc_set(tmp, &bufs[which], cap, tax, false));
+                nxt = bufs[which];
+                bool fell_back = false;
+                size_t n_o = 0;
+                UKM_TRY(ukm_nway_filter(ctx, op == OP_INTER, ks, ns, g + 1, nxt.k, &n_o, &fell_back));
+                for (int q = 0; q < g; ++q) unstage_set(tmp, &in[idx[q]], &G[q]);
+                if (!fell_back) {
+                    if (cur_is_input) {
+                        unstage_set(tmp, &in[0], &cur);
+                        cur_is_input = false;
+                    }
+                    nxt.n = n_o;
+                    bufs[which].n = n_o;
+                    cur = nxt;
+                    which ^= 1;
+                    i = j;
+                    continue;
+                }
+                nway = false;  // inputs that cannot be tiled: file by file from here on
+            }
+        }
         UKM_TRY(stage_set(ctx, tmp, &in[i], tax, &F, &owned, validate && !(op == OP_DIFF && !in[i].sorted)));
         if (op == OP_DIFF && !in[i].sorted) {
             // diff.go:341-367 handles an unsorted subject through a map; here: sort a private copy,
@@ -1136,6 +1196,7 @@ int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags
         bufs[which].n = nxt.n;
         cur = nxt;
         which ^= 1;
+        ++i;
     }
     UKM_TRY(ukm_check_dev_error(ctx, what));
     if (tax) UKM_TRY(materialize_tax(ctx, tmp, &cur));
