@@ -154,6 +154,7 @@ def test_nway_filter_more_than_eight_files(eng, nf, monkeypatch):
 
 
 def test_nway_filter_matches_file_by_file(eng, monkeypatch):
+    monkeypatch.setenv("UKM_NWAY_FILTER", "1")
     files = member_files(1_000_000, 8)
     a_i, a_d = eng.inter(files)[0], eng.diff(files)[0]
     monkeypatch.setenv("UKM_NWAY", "0")
@@ -184,7 +185,10 @@ def test_nway_filter_distributions(eng, monkeypatch):
     cases["with_empty_subject"] = [base[::2].copy(), base[::3].copy(), np.zeros(0, dtype=U64), base[::5].copy(), base[::7].copy()]
     for name, files in cases.items():
         same(eng.inter(files)[0], oracle.inter(files)[0], f"inter {name}")
-        same(eng.diff(files)[0], oracle.diff(files)[0], f"diff {name}")
+        # an EMPTY subject: the reference's worker leaves its loop there (quirk B-5, diff.go:387-392, depends on -j and
+        # on scheduling); the library skips the empty file and goes on, with and without the N-way pass
+        exp = exp_diff(files) if name == "with_empty_subject" else oracle.diff(files)[0]
+        same(eng.diff(files)[0], exp, f"diff {name}")
 
 
 def test_nway_filter_misaligned_device_pointers(eng, monkeypatch):

@@ -72,6 +72,7 @@ def main():
                     os.environ["UKM_NWAY"] = "0"
                 else:
                     os.environ["UKM_NWAY"] = "1"
+                    os.environ["UKM_NWAY_FILTER"] = "1"
                     os.environ["UKM_NWAY_CFG"] = cfg
                 res = {}
 
