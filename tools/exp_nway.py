@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--universe", type=float, default=1e9)
     ap.add_argument("--cfgs", default="off,0,1,2,3,4")
     ap.add_argument("--h2d", action="store_true")
+    ap.add_argument("--only", default="", help="union | inter: run just that part (ncu captures)")
     args = ap.parse_args()
     U = int(args.universe)
     eng = Engine(0)
@@ -41,7 +42,7 @@ def main():
         total = sum(int(f.shape[0]) for f in files)
         out = torch.empty(min(total, U) + 16, dtype=torch.int64, device="cuda")
         ref = None
-        for cfg in args.cfgs.split(","):
+        for cfg in ([] if args.only == "inter" else args.cfgs.split(",")):
             if cfg == "off":
                 os.environ["UKM_NWAY"] = "0"
             else:
@@ -65,7 +66,10 @@ def main():
                                           for k, v in st.items()}}), flush=True)
         # inter / diff: N-way hash filter against the file-by-file passes
         oi = torch.empty(int(files[0].shape[0]) + 16, dtype=torch.int64, device="cuda")
-        for name, fn in (("inter8", eng.inter), ("diff8", eng.diff)):
+        if args.only == "union":
+            eng.close()
+            return
+        for name, fn in ((("inter8", eng.inter),) if args.only == "inter" else (("inter8", eng.inter), ("diff8", eng.diff))):
             ref = None
             for cfg in args.cfgs.split(","):
                 if cfg == "off":
