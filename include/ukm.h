@@ -155,6 +155,12 @@ int ukm_common(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, uint1
  * record r = bases[rec_off[r] .. rec_off[r+1]).  Writes the distinct codes ascending. */
 int ukm_count_seq(ukm_ctx* ctx, const uint8_t* bases, const uint64_t* rec_off, size_t n_rec, int k,
                   unsigned flags, uint64_t max_hash, int where, ukm_span* out);
+/* count -H -W w: sketches.NewMinimizerSketch / NextMinimizer (count.go:100-114, 316-317, 358-359), then the same
+ * scaled filter, dedup and sort as ukm_count_seq.  The codes are the distinct minima of every full window of w
+ * consecutive ntHash values of a record (pinned by analysis/distance/README.md:8: 549 963 on MG1655, k=31, w=15).
+ * UKM_F_HASHED is implied; flags: UKM_F_CANONICAL | UKM_F_CIRCULAR | UKM_F_SCALED. */
+int ukm_count_minimizer(ukm_ctx* ctx, const uint8_t* bases, const uint64_t* rec_off, size_t n_rec, int k, int w,
+                        unsigned flags, uint64_t max_hash, int where, ukm_span* out);
 /* the iterator alone (sketches.NextKmer / NextHash, count.go:361,363; `count --linear`):
  * every k-mer code / hash in record-then-position order, no dedup, no sort. */
 int ukm_kmers_seq(ukm_ctx* ctx, const uint8_t* bases, const uint64_t* rec_off, size_t n_rec, int k,

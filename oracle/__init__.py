@@ -85,6 +85,9 @@ def lib():
         L.orc_count.argtypes = [u8p, u64p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_uint64, C.c_int, u64p, C.c_size_t]
         L.orc_count.restype = C.c_int64
+        L.orc_count_minimizer.argtypes = [u8p, u64p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_uint64, C.c_int, u64p, C.c_size_t]
+        L.orc_count_minimizer.restype = C.c_int64
         L.orc_sm64.argtypes = [C.c_uint64]
         L.orc_sm64.restype = C.c_uint64
         L.orc_universe.argtypes = [C.c_uint64, C.c_size_t, C.c_uint64, C.c_uint64, u64p]
@@ -268,6 +271,17 @@ def count(bases, rec_off, k, canonical=True, hashed=False, circular=False, scale
     out = np.empty(cap, dtype=np.uint64)
     n = _chk(lib().orc_count(b.ctypes.data, ro.ctypes.data, len(ro) - 1, k, int(canonical), int(hashed),
                              int(circular), int(scaled), max_hash, threads, out.ctypes.data, cap))
+    return out[:n].copy()
+
+
+def count_minimizer(bases, rec_off, k, w, canonical=True, circular=False, scaled=False, max_hash=0, threads=1):
+    """`count -H -W w` (count.go:316-317, 358-359): distinct sliding-window minima of the ntHash stream, ascending."""
+    b = np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray)) else np.ascontiguousarray(bases, dtype=np.uint8)
+    ro = _u64(rec_off)
+    cap = len(b) + 1
+    out = np.empty(cap, dtype=np.uint64)
+    n = _chk(lib().orc_count_minimizer(b.ctypes.data, ro.ctypes.data, len(ro) - 1, k, w, int(canonical), int(circular),
+                                       int(scaled), max_hash, threads, out.ctypes.data, cap))
     return out[:n].copy()
 
 

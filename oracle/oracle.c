@@ -745,6 +745,54 @@ int64_t orc_count(const uint8_t* bases, const uint64_t* rec_off, size_t n_rec, i
     return n;
 }
 
+/* count -W w (count.go:100-114 flag handling, 316-317 sketches.NewMinimizerSketch, 358-359
+ * NextMinimizer, then the same scaled filter / dedup map / sort as orc_count).  bio/sketches is
+ * not in the reference tree; what the reference pins is the answer: on E. coli MG1655 with
+ * -k 31 -K -H -W 15 the file holds 549 963 k-mers (analysis/distance/README.md:8,15,39), which is
+ * exactly the number of distinct values of  min(h[i .. i+w-1])  over every FULL window of w
+ * consecutive canonical ntHash values of a record (reproduced; partial windows at the record
+ * ends give 549 965 / 549 967).  So: per record, the sliding-window minimum of the hash stream,
+ * windows never span records, records with fewer than w k-mers contribute nothing.  The code
+ * emitted is the hash itself (-W switches -H on, count.go:105-109). */
+int64_t orc_count_minimizer(const uint8_t* bases, const uint64_t* rec_off, size_t n_rec, int k, int w,
+                            int canonical, int circular, int scaled, uint64_t max_hash,
+                            int threads, uint64_t* out_keys, size_t out_cap) {
+    if (w < 1) return ORC_E_ARG;
+    size_t maxlen = 0, total = 0;
+    for (size_t r = 0; r < n_rec; ++r) {
+        size_t L = (size_t)(rec_off[r + 1] - rec_off[r]);
+        if (L > maxlen) maxlen = L;
+        if (L >= (size_t)k) total += circular ? L : L - (size_t)k + 1;
+    }
+    uint64_t* buf = (uint64_t*)malloc((maxlen + 64) * sizeof(uint64_t));
+    int64_t* dq = (int64_t*)malloc((maxlen + 64) * sizeof(int64_t)); /* monotone deque of positions */
+    if (!buf || !dq) { free(buf); free(dq); return ORC_E_NOMEM; }
+    hmap h;
+    if (hmap_init(&h, total / 4 + 1024)) { free(buf); free(dq); return ORC_E_NOMEM; }
+    for (size_t r = 0; r < n_rec; ++r) {
+        const uint8_t* s = bases + rec_off[r];
+        int64_t L = (int64_t)(rec_off[r + 1] - rec_off[r]);
+        int64_t m = orc_nthash_iter(s, L, k, canonical, circular, buf);
+        if (m < 0) { hmap_free(&h); free(buf); free(dq); return m; }
+        int64_t head = 0, tail = 0;
+        for (int64_t i = 0; i < m; ++i) {
+            while (tail > head && buf[dq[tail - 1]] >= buf[i]) --tail;
+            dq[tail++] = i;
+            if (dq[head] <= i - w) ++head;
+            if (i >= w - 1) {
+                uint64_t mn = buf[dq[head]];
+                if (scaled && mn > max_hash) continue;
+                int fo; hmap_slot(&h, mn, 1, &fo);
+            }
+        }
+    }
+    int64_t n = 0;
+    for (size_t i = 0; i < h.cap; ++i) if (h.used[i]) { if ((size_t)n >= out_cap) { n = ORC_E_ARG; break; } out_keys[n++] = h.keys[i]; }
+    if (n > 0) orc_sort_u64(out_keys, (size_t)n, threads);
+    hmap_free(&h); free(buf); free(dq);
+    return n;
+}
+
 /* ------------------------------------------------------------------------- */
 /* Synthetic-input generators of SURVEY.md section 8(d) (CPU side, counter-based) */
 /* ------------------------------------------------------------------------- */

@@ -229,6 +229,22 @@ func (x *Ctx) FoldSorted(mode int, s Set, flags uint) ([]uint64, []uint32, error
 	}, []Set{s}, len(s.Codes)+2, flags&FTaxid != 0)
 }
 
+// CountMinimizer replaces sketches.NewMinimizerSketch / NextMinimizer + dedup + sort (count.go:316-317, 358-359, 434-436, 581).
+func (x *Ctx) CountMinimizer(bases []byte, recOff []uint64, k, w int, flags uint, maxHash uint64) ([]uint64, error) {
+	codes := make([]uint64, len(bases)+1)
+	out := outSpan(codes, nil)
+	var b *C.uint8_t
+	if len(bases) > 0 {
+		b = (*C.uint8_t)(unsafe.Pointer(&bases[0]))
+	}
+	st := C.ukm_count_minimizer(x.c, b, (*C.uint64_t)(unsafe.Pointer(&recOff[0])), C.size_t(len(recOff)-1), C.int(k), C.int(w),
+		C.uint(flags), C.uint64_t(maxHash), C.UKM_HOST, &out)
+	if e := x.err(st); e != nil {
+		return nil, e
+	}
+	return codes[:int(out.n)], nil
+}
+
 // CountSeq replaces the iterator + dedup map + sort of count.go:314-322, 355-437, 531-595.
 // bases holds the records back to back (fastx strips line breaks); recOff[r]..recOff[r+1] is record r.
 func (x *Ctx) CountSeq(bases []byte, recOff []uint64, k int, flags uint, maxHash uint64) ([]uint64, error) {

@@ -48,6 +48,7 @@ KAT = {
                                 "AGCGCAAAATCCCCAAACATGTA": 2286899379883,
                                 "AACTGATTTTTGATGATGACTCC": 3542156397282},  # README.md:183-186
     "K9_mg1655_k31_nthash_scaled15": 586734,     # analysis/distance/README.md:9,16,44
+    "K12_mg1655_k31_minimizer_w15": 549963,      # analysis/distance/README.md:8,15,39 (count -k 31 -K -H -W 15)
 }
 
 
@@ -120,13 +121,15 @@ def main():
     hs = oracle.count(mg, off, 31, canonical=True, hashed=True)
     sc = oracle.count(mg, off, 31, canonical=True, hashed=True, scaled=True, max_hash=max_hash)
     assert len(sc) == KAT["K9_mg1655_k31_nthash_scaled15"], len(sc)
+    mz = oracle.count_minimizer(mg, off, 31, 15, canonical=True)
+    assert len(mz) == KAT["K12_mg1655_k31_minimizer_w15"], len(mz)
 
     out = dict(KAT)
     out["max_hash_scale15"] = max_hash
     out["digests"] = {
         "mg1655_k23": digest(sets["mg1655"]), "iai39_k23": digest(sets["iai39"]),
         "union": digest(u), "inter": digest(i), "diff": digest(d),
-        "mg1655_k31_nthash": digest(hs), "mg1655_k31_nthash_scaled15": digest(sc),
+        "mg1655_k31_nthash": digest(hs), "mg1655_k31_nthash_scaled15": digest(sc), "mg1655_k31_minimizer_w15": digest(mz),
         "mg1655_k31_kmer_noncanonical": digest(oracle.count(mg, off, 31, canonical=False, hashed=False)),
         "mg1655_k21_circular": digest(oracle.count(mg, off, 21, canonical=True, hashed=False, circular=True)),
     }

@@ -124,58 +124,51 @@ bool run_union(const std::vector<std::vector<uint64_t>>& files, std::vector<uint
             base += padded;
         }
         CHECK(base <= SH::SLOT_E - 8, "segments overflow the slot: %d", base);
-        g.tot = 0;
-        for (int f = 0; f < NWAY; ++f) g.tot += g.n[f];
+        nw_build_tables<NWAY, VT>(&g);
         CHECK(g.tot <= SH::CAP, "tile too large");
-        // log2(NWAY) levels of pairwise unions (nway_kernel<NWOP_UNION>): run r starts at rs[r], holds rl[r] keys
-        int rs[NWAY], rl[NWAY];
-        for (int r = 0; r < NWAY; ++r) { rs[r] = g.off[r]; rl[r] = g.n[r]; }
+        // inner levels
         const uint64_t* src = slot.data();
         uint64_t* dst = X.data();
-        std::vector<uint64_t> staged;
-        for (int l = 1; l <= SH::LEVELS; ++l) {
+        for (int l = 1; l < SH::LEVELS; ++l) {
             const int npairs = NWAY >> l;
-            int tb[NWAY / 2 + 1];
-            tb[0] = 0;
-            for (int m = 0; m < npairs; ++m) tb[m + 1] = tb[m] + (rl[2 * m] + rl[2 * m + 1] + VT - 1) / VT;
-            CHECK(tb[npairs] <= NT, "level %d needs %d threads", l, tb[npairs]);
-            std::vector<unsigned> masks(NT, 0);
-            std::vector<uint64_t> outs((size_t)NT * VT, 0);
+            const int p0 = nw_pair0<NWAY>(l), t0 = nw_tb0<NWAY>(l);
+            CHECK(g.tb[t0 + npairs] <= NT, "level %d needs %d threads", l, g.tb[t0 + npairs]);
             for (int tid = 0; tid < NT; ++tid) {
-                for (int m = 0; m < npairs; ++m) {
-                    if (tid >= tb[m] && tid < tb[m + 1]) {
-                        const int diag = (tid - tb[m]) * VT;
-                        int steps = rl[2 * m] + rl[2 * m + 1] - diag;
-                        CHECK(steps > 0, "thread without work inside a pair");
-                        if (steps > VT) steps = VT;
-                        const uint64_t* A = src + rs[2 * m];
-                        const uint64_t* B = src + rs[2 * m + 1];
-                        const int a = nw_merge_path_g(A, rl[2 * m], B, rl[2 * m + 1], diag);
-                        masks[tid] = nw_walk_unique<VT>(A, rl[2 * m], B, rl[2 * m + 1], a, diag - a, steps, &outs[(size_t)tid * VT]);
-                    }
-                }
+                int j = 0, m;
+                if (npairs == 4) m = nw_find_pair<4>(g.tb + t0, tid, &j);
+                else m = nw_find_pair<2>(g.tb + t0, tid, &j);
+                if (m < 0) continue;
+                const NwPair pr = g.pair[p0 + m];
+                const int diag = j * VT;
+                int steps = pr.lenA + pr.lenB - diag;
+                CHECK(steps > 0, "thread without work inside a pair");
+                if (steps > VT) steps = VT;
+                const uint64_t* A = src + pr.srcA;
+                const uint64_t* B = src + pr.srcB;
+                const int a = nw_merge_path_g(A, pr.lenA, B, pr.lenB, diag);
+                nw_walk_plain<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, dst + pr.dst + diag);
             }
-            // block scan + compacted write (the last level stages its keys for the copy-out instead)
-            std::vector<unsigned> excl(NT + 1, 0);
-            for (int tid = 0; tid < NT; ++tid) excl[tid + 1] = excl[tid] + __builtin_popcount(masks[tid]);
-            if (l == SH::LEVELS) {
-                for (int tid = 0; tid < NT; ++tid)
-                    for (int it = 0; it < VT; ++it)
-                        if (masks[tid] & (1u << it)) staged.push_back(outs[(size_t)tid * VT + it]);
-                break;
-            }
-            CHECK((int)excl[NT] <= SH::CAP, "level output overflows");
-            for (int tid = 0; tid < NT; ++tid) {
-                unsigned o = excl[tid];
-                for (int it = 0; it < VT; ++it)
-                    if (masks[tid] & (1u << it)) dst[o++] = outs[(size_t)tid * VT + it];
-            }
-            int runs[NWAY / 2 + 1];
-            for (int m = 0; m <= npairs; ++m) runs[m] = tb[m] < NT ? (int)excl[tb[m]] : (int)excl[NT];
-            for (int m = 0; m < npairs; ++m) { rs[m] = runs[m]; rl[m] = runs[m + 1] - runs[m]; }
             const uint64_t* tmp = src;
             src = dst;
             dst = const_cast<uint64_t*>(tmp);
+        }
+        // last level
+        const NwPair pr = g.pair[NWAY - 2];
+        const int tot = pr.lenA + pr.lenB;
+        CHECK(tot == g.tot, "totals differ");
+        std::vector<uint64_t> staged;
+        for (int tid = 0; tid < NT; ++tid) {
+            int diag = tid * VT;
+            int steps = tot - diag;
+            if (steps > VT) steps = VT;
+            if (diag > tot) diag = tot;
+            const uint64_t* A = src + pr.srcA;
+            const uint64_t* B = src + pr.srcB;
+            const int a = nw_merge_path_g(A, pr.lenA, B, pr.lenB, diag);
+            uint64_t outk[VT];
+            const unsigned mask = nw_walk_unique<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, outk);
+            for (int it = 0; it < VT; ++it)
+                if (mask & (1u << it)) staged.push_back(outk[it]);
         }
         for (uint64_t v : staged) CHECK(v != 0xDEADBEEFDEADBEEFull || true, "poison");
         out->insert(out->end(), staged.begin(), staged.end());

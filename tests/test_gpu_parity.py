@@ -484,6 +484,33 @@ def test_kat_k8_k9_nthash_on_gpu(eng, kat, genomes):
     assert digest(eng.count(mg, one_record(mg), 21, canonical=True, circular=True)) == kat["digests"]["mg1655_k21_circular"]
 
 
+def test_kat_k12_minimizer_on_gpu(eng, kat, genomes):
+    """analysis/distance/README.md:8: `count -k 31 -K -H -W 15` on MG1655 = 549 963 k-mers."""
+    mg = genomes["mg1655"]
+    mz = eng.count_minimizer(mg, one_record(mg), 31, 15, canonical=True)
+    assert len(mz) == 549963 and digest(mz) == kat["digests"]["mg1655_k31_minimizer_w15"]
+
+
+@pytest.mark.parametrize("canonical", [False, True])
+@pytest.mark.parametrize("circular", [False, True])
+def test_minimizer_multi_record(eng, canonical, circular):
+    """count -W: ragged records (empty, shorter than k, fewer than w k-mers), several windows, the scaled filter;
+    windows never span records."""
+    r = rng(43)
+    lens = [0, 5, 30, 31, 32, 45, 46, 100, 17_408, 17_409 + 14, 40_000, 1, 69, 0, 250_000]
+    recs = [r.choice(np.frombuffer(b"ACGTacgtN", dtype=np.uint8), L).astype(np.uint8) for L in lens]
+    bases = np.concatenate(recs)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(U64)
+    mh = int(float(2**64 - 1) / 4.0)
+    for k, w in ((31, 15), (31, 1), (21, 2), (31, 16), (33, 50), (31, 300_000)):
+        exp = oracle.count_minimizer(bases, off, k, w, canonical=canonical, circular=circular)
+        same(eng.count_minimizer(bases, off, k, w, canonical=canonical, circular=circular), exp, f"minimizer k={k} w={w}")
+    exp = oracle.count_minimizer(bases, off, 31, 15, canonical=canonical, circular=circular, scaled=True, max_hash=mh)
+    same(eng.count_minimizer(bases, off, 31, 15, canonical=canonical, circular=circular, scaled=True, max_hash=mh), exp, "minimizer scaled")
+    same(eng.count_minimizer(bases, off, 31, 1, canonical=canonical, circular=circular),
+         eng.count(bases, off, 31, canonical=canonical, hashed=True, circular=circular), "w=1 is the plain hashed count")
+
+
 @pytest.mark.parametrize("hashed", [False, True])
 @pytest.mark.parametrize("canonical", [False, True])
 @pytest.mark.parametrize("circular", [False, True])

@@ -74,6 +74,36 @@ def test_k9_scaled_minhash_whole_genome(kat, genomes):
     assert len(sc) == kat["K9_mg1655_k31_nthash_scaled15"] == 586734
 
 
+def test_k12_minimizer_whole_genome(kat, genomes):
+    """analysis/distance/README.md:8,15,39: `count -k 31 -K -H -W 15` on MG1655 holds 549 963 k-mers."""
+    mg = genomes["mg1655"]
+    off = np.array([0, len(mg)], dtype=np.uint64)
+    mz = oracle.count_minimizer(mg, off, 31, 15, canonical=True)
+    assert len(mz) == kat["K12_mg1655_k31_minimizer_w15"] == 549963
+    assert digest(mz) == kat["digests"]["mg1655_k31_minimizer_w15"]
+
+
+def test_minimizer_semantics_small():
+    """w = 1 is the plain hashed count; windows never span records; a record with fewer than w k-mers gives nothing."""
+    r = np.random.default_rng(5)
+    recs = [r.choice(np.frombuffer(b"ACGT", dtype=np.uint8), L).astype(np.uint8) for L in (0, 40, 31, 45, 2000, 33)]
+    bases = np.concatenate(recs)
+    off = np.concatenate([[0], np.cumsum([len(x) for x in recs])]).astype(np.uint64)
+    k = 31
+    assert np.array_equal(oracle.count_minimizer(bases, off, k, 1), oracle.count(bases, off, k, canonical=True, hashed=True))
+    for w in (2, 5, 15, 100):
+        exp = set()
+        for s in recs:
+            h = oracle.nthash_iter(s, k, canonical=True) if len(s) >= k else np.zeros(0, dtype=np.uint64)
+            for i in range(0, len(h) - w + 1):
+                exp.add(int(h[i:i + w].min()))
+        got = oracle.count_minimizer(bases, off, k, w)
+        assert np.array_equal(got, np.array(sorted(exp), dtype=np.uint64)), w
+    mh = int(float(2**64 - 1) / 3.0)
+    full = oracle.count_minimizer(bases, off, k, 5)
+    assert np.array_equal(oracle.count_minimizer(bases, off, k, 5, scaled=True, max_hash=mh), full[full <= np.uint64(mh)])
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference testdata not present on this box")
 def test_k3_and_fixture_matches_reference_files(kat, genomes):
     """Against the reference's own files: K3 (third genome) and that the committed 2-bit

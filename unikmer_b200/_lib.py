@@ -22,7 +22,7 @@ SYMBOLS = [
     "ukm_set_taxonomy", "ukm_lca_batch",
     "ukm_sort_u64", "ukm_sort_pairs", "ukm_sort_codetaxid16",
     "ukm_fold_sorted", "ukm_merge_sorted", "ukm_union", "ukm_inter", "ukm_diff", "ukm_common",
-    "ukm_count_seq", "ukm_kmers_seq",
+    "ukm_count_seq", "ukm_kmers_seq", "ukm_count_minimizer",
     "ukm_partition_sorted", "ukm_check_sorted_unique",
     "ukm_synth_random_keys", "ukm_synth_member_file", "ukm_synth_bases",
 ]
@@ -77,6 +77,7 @@ def load():
         "ukm_diff": ([vp, SP, i, u, SP], i), "ukm_common": ([vp, SP, i, u, C.c_uint16, SP], i),
         "ukm_count_seq": ([vp, vp, vp, sz, i, u, u64, i, SP], i),
         "ukm_kmers_seq": ([vp, vp, vp, sz, i, u, u64, i, SP], i),
+        "ukm_count_minimizer": ([vp, vp, vp, sz, i, i, u, u64, i, SP], i),
         "ukm_partition_sorted": ([vp, SP, vp, i, vp], i), "ukm_check_sorted_unique": ([vp, SP], i),
         "ukm_synth_random_keys": ([vp, u64, sz, u64, vp], i),
         "ukm_synth_member_file": ([vp, u64, sz, u64, u64, u64, i, vp, C.POINTER(sz)], i),

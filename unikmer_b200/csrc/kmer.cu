@@ -238,6 +238,45 @@ struct LeGen {
     }
 };
 
+// count -W w: one value per FULL window of w consecutive hashes of a record (sketches.NewMinimizerSketch /
+// NextMinimizer, count.go:316-317,358-359): position i holds min(h[i .. i+w-1]); it is kept when it differs from
+// the window before it (the dedup map of count.go:434-436 would drop the repeat anyway -- this only spares the
+// sort 90% of its input).  Windows never span records.  Neighbouring threads read overlapping hashes: L1 serves them.
+struct MinimizerGen {
+    const uint64_t* h;
+    const unsigned long long* out_off;  // first hash of every record, n_rec + 1 entries
+    int n_rec;
+    int w;
+    int scaled;
+    uint64_t max_hash;
+    __device__ __forceinline__ uint64_t operator()(size_t i, bool* keep) const {
+        int lo = 0, hi = n_rec;  // record of hash i: the last r with out_off[r] <= i
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (out_off[mid] <= i) lo = mid;
+            else hi = mid;
+        }
+        const unsigned long long start = out_off[lo], end = out_off[lo + 1];
+        *keep = false;
+        if (i + (size_t)w > end) return 0;  // not a full window
+        uint64_t m1 = ~0ull;                // min of h[i .. i+w-2], shared with the window before
+        for (int j = 0; j + 1 < w; ++j) {
+            const uint64_t v = h[i + j];
+            m1 = v < m1 ? v : m1;
+        }
+        const uint64_t last = h[i + w - 1];
+        const uint64_t m = m1 < last ? m1 : last;
+        bool k = true;
+        if (i > start) {
+            const uint64_t p = h[i - 1];
+            k = m != (p < m1 ? p : m1);
+        }
+        if (scaled && m > max_hash) k = false;  // count.go:373
+        *keep = k;
+        return m;
+    }
+};
+
 // sequences staged on the device + the per-record output offsets
 struct Prepared {
     KmerArgs a;
@@ -478,4 +517,37 @@ extern "C" int ukm_count_seq(ukm_ctx* ctx, const uint8_t* bases, const uint64_t*
         }
     }
     return ukm_fail(ctx, UKM_E_INTERNAL, "ukm_count_seq: key ranges too skewed for the pass buffers");
+}
+
+// count -H -W w (count.go:100-114, 316-317, 358-359): the distinct sliding-window minima of the ntHash stream of
+// every record, ascending.  hashes -> window minima that differ from their predecessor -> sort -> unique.
+extern "C" int ukm_count_minimizer(ukm_ctx* ctx, const uint8_t* bases, const uint64_t* rec_off, size_t n_rec, int k, int w,
+                                   unsigned flags, uint64_t max_hash, int where, ukm_span* out) {
+    if (!ctx) return UKM_E_ARG;
+    if (!out) return ukm_fail(ctx, UKM_E_ARG, "ukm_count_minimizer: out == NULL");
+    if (w < 1) return ukm_fail(ctx, UKM_E_ARG, "ukm_count_minimizer: w=%d", w);
+    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    flags |= UKM_F_HASHED;  // count.go:105-109: -W switches -H on
+    ukm_tmp tmp(ctx);
+    Prepared P;
+    UKM_TRY(prepare(ctx, tmp, bases, rec_off, n_rec, k, flags, where, &P, "ukm_count_minimizer"));
+    if (P.total == 0) return ukm_deliver(ctx, nullptr, nullptr, 0, out);
+    const size_t n = (size_t)P.total;
+    uint64_t *d_h = nullptr, *d_c = nullptr;
+    UKM_TRY(tmp.alloc(&d_h, n + 2));
+    UKM_TRY(generate_ordered(ctx, P, d_h));
+    UKM_TRY(tmp.alloc(&d_c, n + 2));
+    size_t nc = 0;
+    MinimizerGen g{d_h, P.a.out_off, (int)n_rec, w, (flags & UKM_F_SCALED) ? 1 : 0, max_hash};
+    UKM_TRY(ukm_dev_select(ctx, g, n, d_c, &nc, "minimizer_window", 8.0 * (double)n));
+    tmp.free_now(d_h);
+    UKM_TRY(ukm_check_dev_error(ctx, "ukm_count_minimizer"));
+    if (nc == 0) return ukm_deliver(ctx, nullptr, nullptr, 0, out);
+    UKM_TRY(ukm_dev_sort(ctx, d_c, nullptr, nc, 64));
+    uint64_t* d_u = nullptr;
+    UKM_TRY(tmp.alloc(&d_u, nc + 2));
+    size_t m = 0;
+    UKM_TRY(ukm_dev_fold(ctx, UKM_FOLD_UNIQUE, d_c, nullptr, nc, false, d_u, nullptr, &m));
+    UKM_TRY(ukm_check_dev_error(ctx, "ukm_count_minimizer"));
+    return ukm_deliver(ctx, d_u, nullptr, m, out);
 }

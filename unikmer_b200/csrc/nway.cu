@@ -239,7 +239,6 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
     __shared__ NwGeom<NWAY> s_geom[SLOTS];
     __shared__ const uint64_t* s_fk[NW_MAX];
     __shared__ unsigned s_scan[NW + 2];
-    __shared__ int s_runs[NW_MAX / 2 + 2];
 
     const int G = gridDim.x;
     const int n_my = (p.num_tiles - (int)blockIdx.x + G - 1) / G;  // tiles of this CTA
@@ -307,6 +306,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
             }
             __syncwarp();
             if (lane == 0) {
+                if (OP == NWOP_UNION) nw_build_tables<NWAY, VT>(&s_geom[s]);
                 mbar_expect_tx(&full_bar[s], bytes);  // arrive (release: publishes the plain stores and the tables) + tx count
             }
             __syncwarp();
@@ -387,70 +387,47 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
             if constexpr (OP != NWOP_UNION) {
                 emitmask = nw_filter_tile<OP, NT, VT>(slot, g, s_x, reinterpret_cast<uint32_t*>(s_x + NWF_TABN), tid, p.F.nf, outk);
             } else {
-                // log2(NWAY) levels of pairwise unions.  Every level drops a key that both runs of a pair hold, so
-                // the later levels (and their shared-memory traffic, what bounds this kernel) see fewer keys;
-                // run r of a level starts at rs[r] in `src` and holds rl[r] keys.
-                int rs[NWAY], rl[NWAY];
+            const uint64_t* src = slot;
+            uint64_t* dst = s_x;
+            // inner levels: plain two-way merges, every pair of runs by its own group of threads
 #pragma unroll
-                for (int r = 0; r < NWAY; ++r) {
-                    rs[r] = g.off[r];
-                    rl[r] = g.n[r];
+            for (int l = 1; l < LEVELS; ++l) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int npairs = NWAY >> l;
+                const int p0 = nw_pair0<NWAY>(l), t0 = nw_tb0<NWAY>(l);
+                int j = 0, m;
+                if (npairs == 4) m = nw_find_pair<4>(g.tb + t0, tid, &j);
+                else m = nw_find_pair<2>(g.tb + t0, tid, &j);
+                if (m >= 0) {
+                    const NwPair pr = g.pair[p0 + m];
+                    const int diag = j * VT;
+                    int steps = pr.lenA + pr.lenB - diag;
+                    if (steps > VT) steps = VT;
+                    const uint64_t* A = src + pr.srcA;
+                    const uint64_t* B = src + pr.srcB;
+                    const int a = nw_merge_path_g(A, pr.lenA, B, pr.lenB, diag);
+                    nw_walk_plain<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, dst + pr.dst + diag);
                 }
-                const uint64_t* src = slot;
-                uint64_t* dst = s_x;
-#pragma unroll
-                for (int l = 1; l <= LEVELS; ++l) {
-                    const int npairs = NWAY >> l;
-                    int tb[NWAY / 2 + 1];  // first thread of every pair
-                    tb[0] = 0;
-#pragma unroll
-                    for (int m = 0; m < NWAY / 2; ++m)
-                        if (m < npairs) tb[m + 1] = tb[m] + (rl[2 * m] + rl[2 * m + 1] + VT - 1) / VT;
-                    emitmask = 0;
-#pragma unroll
-                    for (int m = 0; m < NWAY / 2; ++m) {
-                        if (m < npairs && tid >= tb[m] && tid < tb[m + 1]) {
-                            const int diag = (tid - tb[m]) * VT;
-                            int steps = rl[2 * m] + rl[2 * m + 1] - diag;
-                            if (steps > VT) steps = VT;
-                            const uint64_t* A = src + rs[2 * m];
-                            const uint64_t* B = src + rs[2 * m + 1];
-                            const int a = nw_merge_path_g(A, rl[2 * m], B, rl[2 * m + 1], diag);
-                            emitmask = nw_walk_unique<VT>(A, rl[2 * m], B, rl[2 * m + 1], a, diag - a, steps, outk);
-                        }
-                    }
-                    if (l == LEVELS) break;  // the last level's keys are staged below, with the tile's output offset
-                    unsigned level_total;
-                    const unsigned excl = group_excl_scan_u32<NT>((unsigned)__popc(emitmask), (unsigned)tid, s_scan, &level_total, 1);
-                    {
-                        unsigned o = excl;
-#pragma unroll
-                        for (int it = 0; it < VT; ++it)
-                            if (emitmask & (1u << it)) dst[o++] = outk[it];
-                    }
-                    // where the merged runs start: the exclusive prefix of each pair's first thread
-#pragma unroll
-                    for (int m = 0; m <= NWAY / 2; ++m) {
-                        if (m <= npairs) {
-                            if (tb[m] < NT) {
-                                if (tid == tb[m]) s_runs[m] = (int)excl;
-                            } else if (tid == 0) {
-                                s_runs[m] = (int)level_total;
-                            }
-                        }
-                    }
-                    named_bar_sync(1, NT);
-#pragma unroll
-                    for (int m = 0; m < NWAY / 2; ++m) {
-                        if (m < npairs) {
-                            rs[m] = s_runs[m];
-                            rl[m] = s_runs[m + 1] - s_runs[m];
-                        }
-                    }
-                    const uint64_t* t = src;  // level 1: slot -> X; level 2: X -> slot
-                    src = dst;
-                    dst = const_cast<uint64_t*>(t);
-                }
+                named_bar_sync(1, NT);
+                // level 1: slot -> X; level 2: X -> slot
+                const uint64_t* t = src;
+                src = dst;
+                dst = const_cast<uint64_t*>(t);
+            }
+            // last level: merge into registers, keep the first key of every run of equal keys
+            {
+                const NwPair pr = g.pair[NWAY - 2];
+                const int tot = pr.lenA + pr.lenB;
+                int diag = tid * VT;
+                int steps = tot - diag;
+                if (steps > VT) steps = VT;
+                if (diag > tot) diag = tot;
+                const uint64_t* A = src + pr.srcA;
+                const uint64_t* B = src + pr.srcB;
+                const int a = nw_merge_path_g(A, pr.lenA, B, pr.lenB, diag);
+                emitmask = nw_walk_unique<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, outk);
+            }
             }  // union
             unsigned tile_total;
             off = group_excl_scan_u32<NT>((unsigned)__popc(emitmask), (unsigned)tid, s_scan, &tile_total, 1);

@@ -313,6 +313,13 @@ class Engine:
         return self._seq_call(self.lib.ukm_count_seq, bases, rec_off, k,
                               self._count_flags(canonical, hashed, circular, scaled), max_hash)
 
+    def count_minimizer(self, bases, rec_off, k: int, w: int, canonical: bool = True, circular: bool = False,
+                        scaled: bool = False, max_hash: int = 0):
+        """`unikmer count -k K -K -H -W w -s` (count.go:316-317, 358-359): distinct window minima of the ntHash stream."""
+        def fn(ctx, b, ro, n_rec, k_, flags, mh, where, out):
+            return self.lib.ukm_count_minimizer(ctx, b, ro, n_rec, k_, w, flags, mh, where, out)
+        return self._seq_call(fn, bases, rec_off, k, self._count_flags(canonical, True, circular, scaled), max_hash)
+
     def kmers(self, bases, rec_off, k: int, canonical: bool = True, hashed: bool = False, circular: bool = False,
               scaled: bool = False, max_hash: int = 0):
         """The iterator alone (`count --linear`): every code in record-then-position order."""
