@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="key ranges of the streamed end-to-end step")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N>1: NVLink peer pulls (copy engines, overlapped) or one NCCL all-to-all-v")
     args = ap.parse_args()
     args.universe, args.ref_universe, args.cpu_universe = int(args.universe), int(args.ref_universe), int(args.cpu_universe)
@@ -355,6 +356,47 @@ def main():
                     c = eng.union(d, out=ho_u)[0]
                     return a.shape[0], b.shape[0], c.shape[0]
 
+                copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+                NCH = args.e2e_chunks
+
+                def e2e_step_streamed():
+                    # The same step as a stream of key ranges (all three operations are key-local): the slices of range
+                    # c+1 cross PCIe while range c is computed and the results of range c-1 travel back, so the two PCIe
+                    # directions and the kernels overlap.  Every input byte is still uploaded exactly once per step.
+                    # Ranges = quantiles of file 0 (host binary searches, inside the timed region).
+                    hn = [h.numpy().view(np.uint64) for h in order]
+                    cuts = [hn[0][len(hn[0]) * c // NCH] for c in range(1, NCH)]
+                    offs = [np.concatenate([[0], np.searchsorted(a, np.array(cuts, dtype=np.uint64)), [len(a)]]).astype(np.int64)
+                            for a in hn]
+                    keep, wi, wd, wu = [], 0, 0, 0
+
+                    def upload(c):
+                        with torch.cuda.stream(copy_in):
+                            d = [order[f][int(offs[f][c]):int(offs[f][c + 1])].to(dev, non_blocking=True) for f in range(N_FILES)]
+                            ev = torch.cuda.Event()
+                            ev.record(copy_in)
+                        return d, ev
+                    nxt = upload(0)
+                    for c in range(NCH):
+                        d, ev = nxt
+                        if c + 1 < NCH:
+                            nxt = upload(c + 1)  # enqueued before the (host-blocking) calls of range c
+                        stream.wait_event(ev)
+                        a = eng.inter(d)[0]
+                        b = eng.diff(d)[0]
+                        u = eng.union(d)[0]
+                        done = torch.cuda.Event()
+                        done.record(stream)
+                        copy_out.wait_event(done)
+                        with torch.cuda.stream(copy_out):
+                            ho_i[wi:wi + a.shape[0]].copy_(a, non_blocking=True)
+                            ho_d[wd:wd + b.shape[0]].copy_(b, non_blocking=True)
+                            ho_u[wu:wu + u.shape[0]].copy_(u, non_blocking=True)
+                        wi, wd, wu = wi + a.shape[0], wd + b.shape[0], wu + u.shape[0]
+                        keep.append((d, a, b, u))  # device buffers stay alive until the copies have run
+                    copy_out.synchronize()
+                    return wi, wd, wu
+
                 def e2e_step_host_spans():
                     # every operation handed HOST spans: each call stages all eight files again (3 x 32 GB H2D)
                     a = eng.inter(order, out=ho_i)[0]
@@ -393,6 +435,24 @@ def main():
                            "ukm_union on the device spans, results delivered into pinned host buffers" if world == 1 else
                            "pinned host -> H2D -> key-range exchange -> device ops -> D2H"}
             if world == 1:
+                # the step as a stream of key ranges: uploads, kernels and downloads overlap
+                e2e_step_streamed()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    ns3 = e2e_step_streamed()
+                torch.cuda.synchronize()
+                w3 = (time.perf_counter() - t0) / args.e2e_steps
+                assert list(ns3) == [n_inter, n_diff, n_union], "streamed e2e results differ from the device-resident run"
+                whole = {k: e2e[k] for k in ("value", "ms_per_step", "path")}
+                if w3 < float(wt.item()):
+                    e2e.update({"value": 3.0 * total_in / w3, "ms_per_step": 1e3 * w3,
+                                "path": f"C ABI from pinned HOST memory, streamed as {NCH} key ranges (quantiles of file 0): the slices of "
+                                        "range c+1 are uploaded while ukm_inter/ukm_diff/ukm_union run on range c and the results of "
+                                        "range c-1 are downloaded into pinned host buffers; every input byte crosses PCIe once per step"})
+                    e2e["whole_files_uploaded_then_computed"] = whole
+                else:
+                    e2e["streamed_key_ranges"] = {"value": 3.0 * total_in / w3, "ms_per_step": 1e3 * w3, "chunks": NCH}
                 # the same step with HOST spans handed to every call (each op uploads all inputs again)
                 e2e_step_host_spans()
                 torch.cuda.synchronize()

@@ -91,7 +91,7 @@ def main():
             ms = timed(stream, run) - copy_ms
             print(json.dumps({"bench": "sort_pairs", "n": m, "ms": ms, "keys_per_s": m / ms * 1e3}), flush=True)
             del src, vals, wk, wv
-        if "kmers" in what or "count" in what:
+        if "kmers" in what or "count" in what or "minimizer" in what:
             L = min(n, 10**9)
             nrec = 10
             bases = torch.cat([eng.synth_bases(r, 0, L // nrec, 5) for r in range(nrec)])
@@ -111,6 +111,12 @@ def main():
                 ms = timed(stream, lambda: eng.count(bases, off, 31, canonical=True, hashed=True), reps=1)
                 eng.stats_enable(False)
                 print(json.dumps({"bench": "count_k31_KH", "bases": L, "ms": ms, "kmers_per_s": L / ms * 1e3,
+                                  "kernels": {k: round(v["ms"], 2) for k, v in eng.stats().items()}}), flush=True)
+            if "minimizer" in what:
+                eng.stats_reset(); eng.stats_enable(True)
+                ms = timed(stream, lambda: eng.count_minimizer(bases, off, 31, 15, canonical=True), reps=1)
+                eng.stats_enable(False)
+                print(json.dumps({"bench": "count_minimizer_k31_w15", "bases": L, "ms": ms, "kmers_per_s": L / ms * 1e3,
                                   "kernels": {k: round(v["ms"], 2) for k, v in eng.stats().items()}}), flush=True)
             del bases
         if "fold" in what:
