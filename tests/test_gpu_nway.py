@@ -26,6 +26,7 @@ def exp_union(files):
 @pytest.mark.parametrize("nf", [2, 3, 4, 5, 7, 8])
 def test_nway_union_shapes(eng, cfg, nf, monkeypatch):
     monkeypatch.setenv("UKM_NWAY_CFG", cfg)
+    monkeypatch.setenv("UKM_NWAY_FORCE", "1")  # two sets go to the two-way pipeline by default
     for N in (3_000, 250_000, 2_500_000):
         files = member_files(N, nf)
         same(eng.union(files)[0], oracle.union(files)[0], f"union cfg {cfg} nf {nf} N {N}")

@@ -64,18 +64,37 @@ lines = [f"# {tag}: ncu launch list of `python bench.py --steps 1 --warmup 1 --n
          "| kernel | launches | total ms | share | DRAM read GB | DRAM write GB |", "|---|---:|---:|---:|---:|---:|"]
 for k, a in agg.items():
     lines.append(f"| `{k}` | {a['n']} | {a['ms']:.3f} | {a['ms'] / tot * 100:.1f}% | {a['rd'] / 1e9:.2f} | {a['wr'] / 1e9:.2f} |")
-setop = [d for d in L if d["kernel"].startswith(("setop_", "search_partition"))]
+setop = [d for d in L if d["kernel"].startswith(("setop_", "search_partition", "nway_"))]
 so_ms = sum(d.get("ms", 0) for d in setop)
-lines += ["", f"set-operation kernels (merge pipeline + search + partitions): {so_ms:.2f} ms of {tot:.2f} ms = {so_ms / tot * 100:.1f}% "
-          "of all GPU time in the run (the rest is the synthetic input generator `select_kernel<MemberGen>`, outside the timed region)."]
+lines += ["", f"set-operation kernels (N-way union + its partition, two-way passes, searches, partitions): {so_ms:.2f} ms of {tot:.2f} ms = "
+          f"{so_ms / tot * 100:.1f}% of all GPU time in the run (the rest is the synthetic input generator `select_kernel<MemberGen>`, "
+          "outside the timed region)."]
 open(os.path.join(PROF, f"{tag}_launch_summary.md"), "w").write("\n".join(lines) + "\n")
 
-# dram traffic per set-op pass (one pass = partition + kernel = one stats scope in bench.py)
-main = [d for d in setop if not d["kernel"].endswith("partition_kernel")]
-traffic = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in setop) / max(len(main), 1)
-json.dump({"dram_bytes_per_launch": traffic, "launches": len(main),
-           "source": f"profiles/{tag}_launches.csv (dram__bytes_read.sum + dram__bytes_write.sum over all set-op kernels / passes)"},
-          open(os.path.join(PROF, "setop_ncu_traffic.json"), "w"), indent=1)
+
+# dram traffic per stats scope of bench.py (= one N-way operation, or one two-way pass of inter / diff)
+def dram(ds):
+    return sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in ds)
+
+
+def fam(pred):
+    return [d for d in L if pred(d["kernel"])]
+
+
+traffic = {}
+nw_union = fam(lambda k: k.startswith("nway_kernel<0"))
+if nw_union:
+    # the partition / check launches belong to the union calls (inter / diff run file by file by default)
+    aux = fam(lambda k: k.startswith(("nway_partition_kernel", "nway_check_kernel")))
+    traffic["setop_union_nway"] = {"dram_bytes_per_launch": (dram(nw_union) + dram(aux)) / len(nw_union), "launches": len(nw_union),
+                                   "kernels": "nway_partition_kernel x3 + nway_check_kernel + nway_kernel<UNION>"}
+for op, name in ((0, "setop_inter"), (1, "setop_diff"), (2, "setop_union")):
+    main = fam(lambda k, op=op: k.startswith((f"setop_pipe_kernel<{op},", f"setop_search_kernel<{op},", f"setop_fast_kernel<{op},", f"setop_kernel<{op},")))
+    if main:
+        traffic[name] = {"dram_bytes_per_launch": dram(main) / len(main), "launches": len(main),
+                         "kernels": "two-way pass kernels only (their partition kernels are shared between inter and diff in the list)"}
+traffic["source"] = f"profiles/{tag}_launches.csv (dram__bytes_read.sum + dram__bytes_write.sum per launch, summed per operation / pass)"
+json.dump(traffic, open(os.path.join(PROF, "setop_ncu_traffic.json"), "w"), indent=1)
 
 # --set full captures -> key metrics
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -84,7 +103,12 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
-for rep, title in (("setop_union_prof", "setop_pipe_kernel (union passes, 1e9 k-mers in)"), ("onesweep_prof", "onesweep_kernel (one 8-bit pass over 3e8 keys)")):
+KEYS += ["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
+for rep, title in (("nway_union_prof", "nway_kernel<UNION> (one 8-way union of the C3 files, 4e9 k-mers in)"),
+                   ("nway_filter_prof", "nway_kernel<INTER> (opt-in N-way hash filter, 4e9 k-mers in)"),
+                   ("setop_pipe_prof", "setop_pipe_kernel (first two-way passes of inter / diff)"),
+                   ("setop_search_prof", "setop_search_kernel (a later pass of inter: running set looked up in the next file)"),
+                   ("setop_union_prof", "setop_pipe_kernel (union passes, 1e9 k-mers in)"), ("onesweep_prof", "onesweep_kernel (one 8-bit pass over 3e8 keys)")):
     path = os.path.join(OUT, rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
@@ -109,7 +133,7 @@ for rep, title in (("setop_union_prof", "setop_pipe_kernel (union passes, 1e9 k-
     open(os.path.join(PROF, f"{tag}_{rep}.md"), "w").write("\n".join(out) + "\n")
 
 for src, dst in (("bench_full.json", f"{tag}_bench.json"), ("bench_ref.json", f"{tag}_bench_reference.json"), ("microbench.jsonl", f"{tag}_microbench.jsonl"),
-                 ("pytest_gpu.log", f"{tag}_pytest_gpu.log")):
+                 ("pytest_gpu.log", f"{tag}_pytest_gpu.log"), ("exp_nway.jsonl", f"{tag}_exp_nway.jsonl")):
     if os.path.exists(os.path.join(OUT, src)):
         shutil.copy(os.path.join(OUT, src), os.path.join(PROF, dst))
 print("profiles written:", sorted(os.listdir(PROF)))
