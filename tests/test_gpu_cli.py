@@ -120,6 +120,10 @@ def test_count_from_fasta(tmp_path):
     mh = int(float(2**64 - 1) / 15.0)
     assert np.array_equal(codes, oracle.count(bases, off, 31, canonical=True, hashed=True, scaled=True, max_hash=mh))
     assert h.has(unik.SCALED) and h.has(unik.HASHED) and h.scale == 15 and h.max_hash == mh
+    run("count", "-k", "31", "-K", "-W", "15", "-s", "-C", "-o", str(tmp_path / "mz"), fa)  # -W switches hashing on (count.go:105-109)
+    h, codes, _ = unik.read_unik(str(tmp_path / "mz.unik"))
+    assert np.array_equal(codes, oracle.count_minimizer(bases, off, 31, 15, canonical=True))
+    assert h.flag == (unik.SORTED | unik.CANONICAL | unik.HASHED) and h.number == len(codes)
 
 
 def test_taxonomy_and_lca_through_files(tmp_path):

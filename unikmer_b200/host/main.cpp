@@ -50,6 +50,7 @@ struct Options {  // root.go:98-111 persistent flags
     int k = 0;
     bool canonical = false, hashed = false, sorted = false, circular = false, unique = false, repeated = false;
     uint32_t scale = 1, taxid = 0;
+    int minimizer_w = 0;  // count -W
     bool mix_taxid = false, compare_taxid = false;
     int number = 0;
     double proportion = 1.0;
@@ -98,6 +99,8 @@ Options parse(int argc, char** argv, int first) {
         else if (a == "-u" || a == "--unique") o.unique = true;
         else if (a == "-d" || a == "--repeated") o.repeated = true;
         else if (a == "-D" || a == "--scale") o.scale = (uint32_t)strtoul(need(i), nullptr, 10);
+        else if (a == "-W" || a == "--minimizer-w") o.minimizer_w = atoi(need(i));
+        else if (a == "-S" || a == "--syncmer-s") die("count -S (closed syncmers) is not supported by this build: bio/sketches is not pinned by the reference tree");
         else if (a == "-t" || a == "--taxid" || a == "--compare-taxid" || a == "--show-taxid") {
             // `count -t <taxid>` takes a value; `diff -t` / `view -t` are switches
             const std::string cmd = argv[1];
@@ -332,11 +335,16 @@ int cmd_count(Options o) {  // count.go:56-602
         logi(o, "reading sequence file: %s", f.c_str());
         read_fastx(f, bases, rec_off);
     }
+    if (o.minimizer_w > 1) hashed = true;  // count.go:105-109: -W switches -H on
     ukm_ctx* ctx = open_ctx(o);
     unsigned flags = (o.canonical ? UKM_F_CANONICAL : 0) | (hashed ? UKM_F_HASHED : 0) | (o.circular ? UKM_F_CIRCULAR : 0) |
                      (scaled ? UKM_F_SCALED : 0);
     Result r(bases.size() + 1, false);
-    CHECK(ctx, ukm_count_seq(ctx, bases.data(), rec_off.data(), rec_off.size() - 1, o.k, flags, max_hash, UKM_HOST, &r.span));
+    if (o.minimizer_w > 0)  // count.go:316-317, 358-359
+        CHECK(ctx, ukm_count_minimizer(ctx, bases.data(), rec_off.data(), rec_off.size() - 1, o.k, o.minimizer_w, flags, max_hash, UKM_HOST,
+                                       &r.span));
+    else
+        CHECK(ctx, ukm_count_seq(ctx, bases.data(), rec_off.data(), rec_off.size() - 1, o.k, flags, max_hash, UKM_HOST, &r.span));
     uint32_t mode = 0;  // count.go:449-462
     if (o.sorted) mode |= unik::Sorted;
     else if (o.compact && !hashed) mode |= unik::Compact;
@@ -545,7 +553,7 @@ int main(int argc, char** argv) {
                 "unikmer-b200: k-mer set operations on B200 (libukm)\n\n"
                 "usage: unikmer-b200 <count|sort|union|inter|diff|common|view|info> [flags] [files]\n"
                 "flags follow unikmer: -o, -C, -c, -i, -I, --max-taxid, --data-dir, --verbose, --device;\n"
-                "  count: -k -K -H -s --circular -D -t   sort: -u -d   union: -s   inter: -m\n"
+                "  count: -k -K -H -s --circular -D -W -t   sort: -u -d   union: -s   inter: -m\n"
                 "  diff: -s -t   common: -n -p -m   view: -t -N\n");
         return argc < 2 ? 1 : 0;
     }
