@@ -277,6 +277,156 @@ struct MinimizerGen {
     }
 };
 
+// The same selection for windows up to MZ_WMAX, tiled: a CTA stages MZ_TILE + w hashes in shared memory, every
+// thread owns MZ_R consecutive positions and builds their window minima from one pass over the w + MZ_R hashes they
+// span (the part common to all of its windows once, suffix minima on the left, prefix minima on the right), so a
+// position costs (w + MZ_R) / MZ_R shared-memory loads instead of w + 1 global ones.  Compaction as in select_kernel.
+constexpr int MZ_THREADS = 256;
+constexpr int MZ_R = 9;  // odd: the 8-byte accesses of neighbouring threads fall into different banks
+constexpr int MZ_TILE = MZ_THREADS * MZ_R;
+constexpr int MZ_WMAX = 4096;
+
+struct MzArgs {
+    const uint64_t* h;
+    size_t n;
+    const unsigned long long* out_off;
+    int n_rec;
+    int w;
+    int scaled;
+    uint64_t max_hash;
+    uint64_t* out;
+    uint64_t* status;
+    uint32_t* tile_counter;
+    unsigned long long* total_out;
+    int num_tiles;
+    int* err;
+};
+
+__device__ __forceinline__ uint64_t mz_min(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+__global__ void __launch_bounds__(MZ_THREADS) minimizer_kernel(const MzArgs p) {
+    constexpr int NW = MZ_THREADS / 32;
+    extern __shared__ __align__(16) unsigned char mz_smem[];
+    uint64_t* s_x = reinterpret_cast<uint64_t*>(mz_smem);  // s_x[q] = h[t0 - 1 + q], q < MZ_TILE + w + 1
+    uint64_t* s_o = s_x + MZ_TILE + p.w + 1;               // staged output, MZ_TILE
+    __shared__ unsigned s_scan[NW + 2];
+    __shared__ int s_tile;
+    __shared__ unsigned long long s_prefix;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_tile = (int)atomicAdd(p.tile_counter, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const int w = p.w;
+    const size_t t0 = (size_t)tile * MZ_TILE;
+    const int nx = MZ_TILE + w + 1;
+    for (int q = tid; q < nx; q += MZ_THREADS) {
+        const size_t g = t0 + (size_t)q;  // hash index + 1
+        s_x[q] = (g >= 1 && g - 1 < p.n) ? p.h[g - 1] : ~0ull;
+    }
+    __syncthreads();
+    // W[j] = minimum of the window that starts at position i0 - 1 + j  (s_x[q0 + j .. q0 + j + w - 1])
+    const size_t i0 = t0 + (size_t)tid * MZ_R;
+    const int q0 = tid * MZ_R;
+    uint64_t W[MZ_R + 1];
+    if (w > MZ_R) {
+        uint64_t mid = ~0ull;  // s_x[q0 + R .. q0 + w - 1]: inside every one of the R + 1 windows
+        for (int q = q0 + MZ_R; q <= q0 + w - 1; ++q) mid = mz_min(mid, s_x[q]);
+        uint64_t l = ~0ull;
+#pragma unroll
+        for (int j = MZ_R - 1; j >= 0; --j) {
+            l = mz_min(l, s_x[q0 + j]);
+            W[j] = mz_min(l, mid);
+        }
+        W[MZ_R] = mid;
+        uint64_t r = ~0ull;
+#pragma unroll
+        for (int j = 1; j <= MZ_R; ++j) {
+            r = mz_min(r, s_x[q0 + w + j - 1]);
+            W[j] = mz_min(W[j], r);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j <= MZ_R; ++j) {
+            uint64_t m = ~0ull;
+            for (int t = 0; t < w; ++t) m = mz_min(m, s_x[q0 + j + t]);
+            W[j] = m;
+        }
+    }
+    // record of position i0: the last r with out_off[r] <= i0
+    int r = 0;
+    {
+        int lo = 0, hi = p.n_rec;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (p.out_off[mid] <= i0) lo = mid;
+            else hi = mid;
+        }
+        r = lo;
+    }
+    unsigned long long rs = p.out_off[r], re = p.out_off[r + 1];
+    unsigned mask = 0;
+#pragma unroll
+    for (int j = 0; j < MZ_R; ++j) {
+        const size_t i = i0 + (size_t)j;
+        if (i < p.n) {
+            while (i >= re && r + 1 < p.n_rec) {
+                ++r;
+                rs = re;
+                re = p.out_off[r + 1];
+            }
+            bool keep = i >= rs && i + (size_t)w <= re;          // a full window inside the record
+            keep = keep && (i == rs || W[j + 1] != W[j]);        // differs from the window before it
+            if (p.scaled && W[j + 1] > p.max_hash) keep = false;  // count.go:373
+            if (keep) mask |= 1u << j;
+        }
+    }
+    unsigned tile_total;
+    const unsigned off = block_excl_scan_u32<MZ_THREADS>((unsigned)__popc(mask), s_scan, &tile_total);
+    unsigned o = off;
+#pragma unroll
+    for (int j = 0; j < MZ_R; ++j)
+        if (mask & (1u << j)) s_o[o++] = W[j + 1];
+    const unsigned long long pre = tile_exclusive_prefix(p.status, tile, tile_total, p.err, &s_prefix);
+    if (tid == 0 && tile == p.num_tiles - 1) *p.total_out = pre + tile_total;
+    for (unsigned i = tid; i < tile_total; i += MZ_THREADS) p.out[pre + i] = s_o[i];
+}
+
+int minimizer_select(ukm_ctx* ctx, const MinimizerGen& g, size_t n, uint64_t* d_out, size_t* n_out) {
+    *n_out = 0;
+    if (n == 0) return UKM_OK;
+    if (g.w > MZ_WMAX) return ukm_dev_select(ctx, g, n, d_out, n_out, "minimizer_window", 8.0 * (double)n);
+    const int num_tiles = (int)((n + MZ_TILE - 1) / MZ_TILE);
+    const size_t smem = ((size_t)2 * MZ_TILE + (size_t)g.w + 1) * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured) {
+        UKM_CUDA(ctx, cudaFuncSetAttribute(minimizer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(((size_t)2 * MZ_TILE + MZ_WMAX + 1) * sizeof(uint64_t))));
+        configured = true;
+    }
+    ukm_tmp tmp(ctx);
+    uint64_t* d_status = nullptr;
+    UKM_TRY(tmp.alloc(&d_status, (size_t)num_tiles + 4));
+    MzArgs a;
+    a.h = g.h; a.n = n; a.out_off = g.out_off; a.n_rec = g.n_rec; a.w = g.w; a.scaled = g.scaled; a.max_hash = g.max_hash;
+    a.out = d_out;
+    a.status = d_status;
+    a.tile_counter = reinterpret_cast<uint32_t*>(d_status + num_tiles);
+    a.total_out = reinterpret_cast<unsigned long long*>(d_status + num_tiles + 1);
+    a.num_tiles = num_tiles;
+    a.err = ctx->d_err;
+    UKM_CUDA(ctx, cudaMemsetAsync(d_status, 0, ((size_t)num_tiles + 4) * sizeof(uint64_t), ctx->stream));
+    {
+        ukm_stat_scope st(ctx, "minimizer_window", 8.0 * (double)n);
+        minimizer_kernel<<<num_tiles, MZ_THREADS, smem, ctx->stream>>>(a);
+        UKM_LAUNCHED(ctx);
+    }
+    UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, a.total_out, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = (size_t)ctx->h_scratch[0];
+    if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes += 8.0 * (double)*n_out;
+    return UKM_OK;
+}
+
 // sequences staged on the device + the per-record output offsets
 struct Prepared {
     KmerArgs a;
@@ -539,7 +689,7 @@ extern "C" int ukm_count_minimizer(ukm_ctx* ctx, const uint8_t* bases, const uin
     UKM_TRY(tmp.alloc(&d_c, n + 2));
     size_t nc = 0;
     MinimizerGen g{d_h, P.a.out_off, (int)n_rec, w, (flags & UKM_F_SCALED) ? 1 : 0, max_hash};
-    UKM_TRY(ukm_dev_select(ctx, g, n, d_c, &nc, "minimizer_window", 8.0 * (double)n));
+    UKM_TRY(minimizer_select(ctx, g, n, d_c, &nc));
     tmp.free_now(d_h);
     UKM_TRY(ukm_check_dev_error(ctx, "ukm_count_minimizer"));
     if (nc == 0) return ukm_deliver(ctx, nullptr, nullptr, 0, out);
