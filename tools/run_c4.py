@@ -24,7 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--records", type=int, default=100)
     ap.add_argument("--length", type=float, default=1e8)
-    ap.add_argument("--pass-limit", type=float, default=1.5e9)
+    ap.add_argument("--pass-limit", type=float, default=2.5e9)
     args = ap.parse_args()
     R, L = args.records, int(args.length)
     os.environ["UKM_COUNT_PASS"] = str(int(args.pass_limit))
@@ -37,6 +37,14 @@ def main():
             bases[r * L:(r + 1) * L] = eng.synth_bases(r, 0, L, 5)
         off = torch.arange(0, R + 1, dtype=torch.int64, device="cuda") * L
         torch.cuda.synchronize()
+        # a first (cold) call maps the 80 GB output and the pass buffers for the first time; time it, drop the result,
+        # and time the steady state
+        t0 = time.perf_counter()
+        out = eng.count(bases, off, 31, canonical=True, hashed=True)
+        torch.cuda.synchronize()
+        cold_s = time.perf_counter() - t0
+        del out
+        torch.cuda.empty_cache()
         eng.stats_reset()
         eng.stats_enable(True)
         t0 = time.perf_counter()
@@ -64,7 +72,7 @@ def main():
         # every hash of the window must be present in the full result
         present = bool(torch.isin(got.view(torch.int64), u).all().item()) if u.shape[0] < 3_000_000_000 else None
     print(json.dumps({"config": f"C4 count -k 31 -K -H -s, {R} records x {L:.0e} bases", "bases": R * L, "kmers": n_kmers,
-                      "distinct": int(out.shape[0]), "ms": ms, "wall_s": wall, "kmers_per_s": n_kmers / ms * 1e3,
+                      "distinct": int(out.shape[0]), "ms": ms, "wall_s": wall, "cold_first_call_s": cold_s, "kmers_per_s": n_kmers / ms * 1e3,
                       "strictly_increasing": increasing, "window_exact_vs_oracle": exact, "window_subset_of_result": present,
                       "kernels_ms": {k: round(v["ms"], 1) for k, v in st.items()}}))
     if not (increasing and exact):

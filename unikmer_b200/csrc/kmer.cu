@@ -84,11 +84,16 @@ constexpr int KM_STAGE = 256;  // per-warp staging ring of the FILTER mode (flus
 // FILTER = false: every code to out[out_off[r] + position] (record-then-position order).
 // FILTER = true : codes inside [range_lo, range_hi] are compacted warp-wide through a shared-memory ring and
 //                 appended in 1 KB bursts at a global cursor (order is irrelevant: `count` sorts next).
+// The tile's bases are staged as CLASSES (the byte -> class table applied once per base, not once per use); a
+// thread whose 68 starts and their k-1 trailing bases lie inside one record and inside the staged tile -- all but
+// the threads at record or tile seams -- takes a fast path: 32-bit shared-memory indices, no record bookkeeping,
+// one 16-byte seed load per incoming and per outgoing base, codes stored in aligned pairs.
 template <bool HASHED, bool FILTER>
 __global__ void __launch_bounds__(KM_THREADS) kmer_kernel(const KmerArgs p) {
-    __shared__ uint8_t s_b[KM_TILE + KM_HALO + 16];
+    __shared__ uint8_t s_b[KM_TILE + KM_HALO + 16];  // class of every staged base
     __shared__ uint8_t s_lut[256];
     __shared__ uint64_t s_seed[4][8];  // [f_in, f_out(rol k), r_in(rol k-1), r_out(ror 1)][class 0..3, 4..7 = 0]
+    __shared__ ulonglong2 s_in[8], s_out[8];  // {f_in, r_in}[class], {f_out, r_out}[class]: one load per base
     __shared__ uint64_t s_stage[FILTER ? (KM_THREADS / 32) * KM_STAGE : 1];
 
     const int tid = threadIdx.x;
@@ -97,7 +102,9 @@ __global__ void __launch_bounds__(KM_THREADS) kmer_kernel(const KmerArgs p) {
     const size_t tile_end = (B0 + KM_TILE + KM_HALO < p.n_bases) ? B0 + KM_TILE + KM_HALO : p.n_bases;
     const int tile_len = (int)(tile_end - B0);
     build_lut(s_lut);
-    for (int i = tid; i < tile_len; i += KM_THREADS) s_b[i] = p.bases[B0 + i];
+    if (HASHED) {  // ntHash: every byte that is not A C G T(U) contributes 0 -> class 4
+        for (int i = tid; i < 256; i += KM_THREADS) s_lut[i] = s_lut[i] < 4 ? s_lut[i] : 4;
+    }
     if (HASHED && tid < 32) {
         const uint64_t S[4] = {0x3c8bfbb395c60474ull, 0x3193c18562a02b4cull, 0x20323ed082572324ull, 0x295549f54be24456ull};
         int t = tid >> 3, c = tid & 7;
@@ -107,6 +114,12 @@ __global__ void __launch_bounds__(KM_THREADS) kmer_kernel(const KmerArgs p) {
             v = t == 0 ? sf : t == 1 ? rol64d(sf, (unsigned)p.k) : t == 2 ? rol64d(sr, (unsigned)(p.k - 1)) : ror64d(sr, 1);
         }
         s_seed[t][c] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < tile_len; i += KM_THREADS) s_b[i] = s_lut[p.bases[B0 + i]];
+    if (HASHED && tid < 8) {
+        s_in[tid] = make_ulonglong2(s_seed[0][tid], s_seed[2][tid]);
+        s_out[tid] = make_ulonglong2(s_seed[1][tid], s_seed[3][tid]);
     }
     __syncthreads();
 
@@ -140,10 +153,10 @@ __global__ void __launch_bounds__(KM_THREADS) kmer_kernel(const KmerArgs p) {
     uint64_t* stage = s_stage + (FILTER ? (tid >> 5) * KM_STAGE : 0);
     unsigned staged = 0;  // codes waiting in this warp's ring (warp-uniform)
 
-    // base at absolute index q of the current record (q may run past `re` when circular)
+    // class of the base at absolute index q of the current record (q may run past `re` when circular)
     auto fetch = [&](size_t q) -> uint8_t {
         if (q >= re) q = rs + (q - re);
-        return (q >= B0 && q < tile_end) ? s_b[q - B0] : p.bases[q];
+        return (q >= B0 && q < tile_end) ? s_b[q - B0] : s_lut[p.bases[q]];
     };
     // FILTER: append `n` staged codes (n <= KM_STAGE, warp-uniform) at the global cursor
     auto flush = [&](unsigned n) {
@@ -154,62 +167,92 @@ __global__ void __launch_bounds__(KM_THREADS) kmer_kernel(const KmerArgs p) {
             if (base + i < p.cap) p.out[base + i] = stage[i];
         __syncwarp();
     };
+    // first k-mer of a run from scratch: `cls(i)` = class of its i-th base
+    auto init = [&](auto cls) {
+        fw = 0;
+        rv = 0;
+        if (HASHED) {
+            for (int i = 0; i < k; ++i) {
+                const uint8_t c = cls(i);
+                const uint64_t sf = s_seed[0][c];
+                const uint64_t sr = c < 4 ? s_seed[0][3 - c] : 0ull;
+                fw ^= rol64d(sf, (unsigned)(k - 1 - i));
+                rv ^= rol64d(sr, (unsigned)i);
+            }
+        } else {
+            for (int i = 0; i < k; ++i) {
+                const uint8_t c = cls(i);
+                if (c == 255) illegal = true;
+                const uint64_t v = (c >= 4 ? (uint64_t)(c - 4) : (uint64_t)c) & 3u;
+                fw = ((fw << 2) | v) & kmask;
+                rv = (rv >> 2) | ((v ^ 3u) << (2 * (k - 1)));
+            }
+        }
+    };
+    // next k-mer: base of class cin enters, base of class cout leaves
+    auto roll = [&](uint8_t cin, uint8_t cout) {
+        if (HASHED) {
+            const ulonglong2 si = s_in[cin], so = s_out[cout];
+            fw = ((fw << 1) | (fw >> 63)) ^ so.x ^ si.x;
+            rv = ((rv >> 1) | (rv << 63)) ^ so.y ^ si.y;
+        } else {
+            if (cin == 255) illegal = true;
+            const uint64_t v = (cin >= 4 ? (uint64_t)(cin - 4) : (uint64_t)cin) & 3u;
+            fw = ((fw << 2) | v) & kmask;
+            rv = (rv >> 2) | ((v ^ 3u) << (2 * (k - 1)));
+        }
+    };
+
+    // fast path: the whole chunk and its trailing k-1 bases inside one record and inside the staged tile
+    const bool fast = any && b_end == b0 + KM_CHUNK && b0 + KM_CHUNK + (size_t)k - 1 <= re && b0 + KM_CHUNK + (size_t)k - 1 <= tile_end;
+    const int li = (int)(b0 - B0);  // shared-memory index of the chunk's first base
+    uint64_t* const op = FILTER ? nullptr : p.out + (obase + (b0 - rs));
+    const bool op_odd = (reinterpret_cast<uintptr_t>(op) & 15u) != 0;  // the first code is the second half of an aligned pair
+    uint64_t pend = 0;  // first code of an aligned pair, waiting for its partner
 
     for (int j = 0; j < KM_CHUNK; ++j) {  // uniform trip count: the FILTER mode votes warp-wide every step
-        const size_t b = b0 + (size_t)j;
         bool emit = false;
         uint64_t code = 0;
-        if (b < b_end) {
-            while (b >= re) {
-                ++r;
-                rs = re;
-                re = p.rec_off[r + 1];
-                obase = p.out_off[r];
-                have = false;
-            }
-            const size_t L = re - rs;
-            if (L < (size_t)k || (!p.circular && b + k > re)) {
-                have = false;
-            } else {
-                if (!have) {
-                    fw = 0;
-                    rv = 0;
-                    if (HASHED) {
-                        for (int i = 0; i < k; ++i) {
-                            uint8_t c = s_lut[fetch(b + i)];
-                            uint64_t sf = c < 4 ? s_seed[0][c] : 0ull;
-                            uint64_t sr = c < 4 ? s_seed[0][3 - c] : 0ull;
-                            fw ^= rol64d(sf, (unsigned)(k - 1 - i));
-                            rv ^= rol64d(sr, (unsigned)i);
-                        }
-                    } else {
-                        for (int i = 0; i < k; ++i) {
-                            uint8_t c = s_lut[fetch(b + i)];
-                            if (c == 255) illegal = true;
-                            uint64_t v = (c >= 4 ? (uint64_t)(c - 4) : (uint64_t)c) & 3u;
-                            fw = ((fw << 2) | v) & kmask;
-                            rv = (rv >> 2) | ((v ^ 3u) << (2 * (k - 1)));
-                        }
-                    }
-                    have = true;
+        if (fast) {
+            if (j == 0) init([&](int i) { return s_b[li + i]; });
+            else roll(s_b[li + j + k - 1], s_b[li + j - 1]);
+            code = (p.canonical && rv < fw) ? rv : fw;
+            emit = true;
+            if (!FILTER) {
+                // codes j, j+1 form an aligned 16-byte pair when (j odd) == op_odd ... store pairs, singles at the ends
+                const bool second = ((j & 1) != 0) != op_odd;  // this code completes a pair that started at j - 1
+                if (second && j > 0) {
+                    st_stream_u64x2(reinterpret_cast<ulonglong2*>(op + j - 1), make_ulonglong2(pend, code));
+                } else if (!second && j + 1 < KM_CHUNK) {
+                    pend = code;
                 } else {
-                    uint8_t cin = s_lut[fetch(b + k - 1)];
-                    if (HASHED) {
-                        uint8_t cout = s_lut[fetch(b - 1)];
-                        uint64_t fi = cin < 4 ? s_seed[0][cin] : 0ull, fo = cout < 4 ? s_seed[1][cout] : 0ull;
-                        uint64_t ri = cin < 4 ? s_seed[2][cin] : 0ull, ro = cout < 4 ? s_seed[3][cout] : 0ull;
-                        fw = rol64d(fw, 1) ^ fo ^ fi;
-                        rv = ror64d(rv, 1) ^ ro ^ ri;
-                    } else {
-                        if (cin == 255) illegal = true;
-                        uint64_t v = (cin >= 4 ? (uint64_t)(cin - 4) : (uint64_t)cin) & 3u;
-                        fw = ((fw << 2) | v) & kmask;
-                        rv = (rv >> 2) | ((v ^ 3u) << (2 * (k - 1)));
-                    }
+                    op[j] = code;  // j == 0 completing a pair that belongs to the thread before, or the last, unpaired code
                 }
-                code = (p.canonical && rv < fw) ? rv : fw;
-                emit = true;
-                if (!FILTER) p.out[obase + (b - rs)] = code;
+            }
+        } else {
+            const size_t b = b0 + (size_t)j;
+            if (b < b_end) {
+                while (b >= re) {
+                    ++r;
+                    rs = re;
+                    re = p.rec_off[r + 1];
+                    obase = p.out_off[r];
+                    have = false;
+                }
+                const size_t L = re - rs;
+                if (L < (size_t)k || (!p.circular && b + k > re)) {
+                    have = false;
+                } else {
+                    if (!have) {
+                        init([&](int i) { return fetch(b + i); });
+                        have = true;
+                    } else {
+                        roll(fetch(b + k - 1), fetch(b - 1));
+                    }
+                    code = (p.canonical && rv < fw) ? rv : fw;
+                    emit = true;
+                    if (!FILTER) p.out[obase + (b - rs)] = code;
+                }
             }
         }
         if (FILTER) {
