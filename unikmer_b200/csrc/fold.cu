@@ -13,6 +13,7 @@ namespace {
 constexpr int FD_THREADS = 256;
 constexpr int FD_ITEMS = 8;
 constexpr int FD_TILE = FD_THREADS * FD_ITEMS;
+#define FD_P(q) ((q) + (((q) + 7) >> 3))  // slot of halo-relative index q (q = element index + 1); FD_P(8t+1 .. 8t+8) are consecutive
 
 template <int MODE, bool TAX>
 __global__ void __launch_bounds__(FD_THREADS)
@@ -20,7 +21,10 @@ __global__ void __launch_bounds__(FD_THREADS)
                 uint32_t* __restrict__ outT, uint64_t* __restrict__ status, uint32_t* __restrict__ tile_counter,
                 unsigned long long* __restrict__ total_out, int num_tiles, TaxDev tax, int* __restrict__ err) {
     constexpr int NW = FD_THREADS / 32;
-    __shared__ uint64_t s_k[FD_TILE + 2];      // [0] = left halo, [1..TILE] tile, [TILE+1] right halo
+    // tile element i lives at s_k[FD_P(i + 1)]: one pad slot per 8 elements, so that the blocked walk (thread t owns
+    // elements 8t .. 8t+7) strides 9 slots across a warp and every 8-byte access hits its own bank pair (the unpadded
+    // layout was an 8-way conflict on each of the three loads per key: half of the kernel's time)
+    __shared__ uint64_t s_k[FD_TILE + FD_TILE / 8 + 4];  // FD_P(0) = left halo, FD_P(1..TILE) tile, FD_P(TILE+1) right halo
     __shared__ uint64_t s_ok[FD_TILE + 2];     // staging: a tile emits at most valid+1 (a run emitting 2 has >= 2 elements)
     __shared__ uint32_t s_ot[TAX ? FD_TILE + 2 : 1];
     __shared__ unsigned s_scan[NW + 2];
@@ -34,11 +38,11 @@ __global__ void __launch_bounds__(FD_THREADS)
     const size_t base = (size_t)tile * FD_TILE;
     const int valid = (n - base) < (size_t)FD_TILE ? (int)(n - base) : FD_TILE;
 
-    for (int i = tid; i < valid; i += FD_THREADS) s_k[1 + i] = ld_stream_u64(keys + base + i);
+    for (int i = tid; i < valid; i += FD_THREADS) s_k[FD_P(1 + i)] = ld_stream_u64(keys + base + i);
     if (tid == 0) {
         // halos: has_left / has_right say whether a neighbour exists at all
-        s_k[0] = base > 0 ? keys[base - 1] : 0;
-        s_k[1 + valid] = (base + valid < n) ? keys[base + valid] : 0;
+        s_k[FD_P(0)] = base > 0 ? keys[base - 1] : 0;
+        s_k[FD_P(1 + valid)] = (base + valid < n) ? keys[base + valid] : 0;
     }
     __syncthreads();
     const bool has_left = base > 0;
@@ -54,9 +58,9 @@ __global__ void __launch_bounds__(FD_THREADS)
         unsigned e = 0;
         lca[j] = 0;
         if (i < valid) {
-            const uint64_t k = s_k[1 + i];
-            const bool head = (i > 0 || has_left) ? (s_k[i] != k) : true;
-            const bool next_same = (i + 1 < valid || has_right) ? (s_k[2 + i] == k) : false;
+            const uint64_t k = s_k[FD_P(1 + i)];
+            const bool head = (i > 0 || has_left) ? (s_k[FD_P(i)] != k) : true;
+            const bool next_same = (i + 1 < valid || has_right) ? (s_k[FD_P(2 + i)] == k) : false;
             if (head) {
                 if (MODE == UKM_FOLD_UNIQUE) e = 1;
                 else if (MODE == UKM_FOLD_REPEATED_FINAL) e = next_same ? 1 : 0;
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(FD_THREADS)
         for (int j = 0; j < FD_ITEMS; ++j) {
             const unsigned e = (emit2 >> (2 * j)) & 3u;
             if (e) {
-                const uint64_t k = s_k[1 + tid * FD_ITEMS + j];
+                const uint64_t k = s_k[FD_P(1 + tid * FD_ITEMS + j)];
                 s_ok[o] = k;
                 if (TAX) s_ot[o] = lca[j];
                 ++o;
