@@ -3,7 +3,7 @@
 // Replaces the hash-set union of union.go:186-208 and its key sort (union.go:260-305) -- and the levels of the
 // two-way merge tree this library used before -- with ONE pass over the inputs: the key space is cut into tiles
 // of ~TILE elements summed over all files (partition kernels below: multi-sequence selection on
-// rank(K) = sum_f lower_bound(F_f, K), regula falsi + bisection, coarse then fine), every tile is brought into
+// rank(K) = sum_f lower_bound(F_f, K) with pivots taken from the data, three levels), every tile is brought into
 // shared memory with one 1-D TMA bulk copy per file and merged there in log2(N) levels of two-way merge-path
 // walks; the last level drops equal neighbours (the same k-mer in several files) and the distinct keys leave
 // through the same deferred, coalesced copy-out as the two-way pipeline (setops.cu).  HBM traffic is the
@@ -392,8 +392,6 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
             // inner levels: plain two-way merges, every pair of runs by its own group of threads
 #pragma unroll
             for (int l = 1; l < LEVELS; ++l) {
-                constexpr int dummy = 0;
-                (void)dummy;
                 const int npairs = NWAY >> l;
                 const int p0 = nw_pair0<NWAY>(l), t0 = nw_tb0<NWAY>(l);
                 int j = 0, m;

@@ -22,8 +22,6 @@
 #endif
 
 constexpr int NW_MAX = 8;       // files per pass
-constexpr int NW_COARSE = 32;   // tiles per coarse partition chunk
-constexpr int NW_MAX_PAIRS = 7; // 4 + 2 + 1 two-way merges per tile at N = 8
 
 // ---------------------------------------------------------------------------------------------------
 // partition: cut every file at lower_bound(key); rank = total elements below the cut
