@@ -61,7 +61,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -252,6 +252,11 @@ def main():
                 lvl = [eng.union(lvl[q:q + 2])[0] for q in range(0, len(lvl), 2)]
             return ci, cd, lvl[0]
 
+        # clocks / throttle reasons are sampled from before the warm-up until the end of the timed region (nvidia-smi
+        # needs ~0.1 s before its first line; at N = 8 the timed region itself is shorter than that)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
         res = None
         for _ in range(args.warmup):
             res = step()
@@ -259,9 +264,6 @@ def main():
         eng.stats_reset()
         eng.stats_enable(True)
         launches0 = eng.launch_count()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
