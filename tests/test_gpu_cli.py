@@ -74,6 +74,41 @@ def test_k10_union_s_equals_sort_u(c1):
     assert hp.number == len(A) + len(B) and np.array_equal(cp, np.sort(np.concatenate([A, B])))
 
 
+def test_split_then_merge_is_the_external_sort(tmp_path):
+    """`split -m` (stage 1 of sort -m: sorted chunk files, util-sort.go:35-190) + `merge` (mergeChunksFile,
+    util-sort.go:227-606) give what the in-memory sort gives: plain, -u and -d (K10: README.md:222-229)."""
+    r = np.random.default_rng(9)
+    keys = r.integers(0, 40_000, 100_000).astype(U64)  # many duplicates, also across chunks
+    src = str(tmp_path / "in.unik")
+    unik.write_unik(src, unik.Header(k=31, flag=unik.CANONICAL, number=len(keys)), keys, compress=False)
+    uniq, cnt = np.unique(keys, return_counts=True)
+    for flag, exp in ((None, np.sort(keys)), ("-u", uniq), ("-d", uniq[cnt >= 2])):
+        d = str(tmp_path / f"chunks{flag or ''}")
+        extra = [flag] if flag else []
+        run("split", "-m", "16K", "-O", d, *extra, src)  # 16K = 16384 k-mers per chunk (util.go:291)
+        chunks = sorted(os.listdir(d))
+        assert chunks == [f"chunk_{i:03d}.unik" for i in range(7)]
+        seen = []
+        for c in chunks:
+            h, codes, _ = unik.read_unik(os.path.join(d, c))
+            assert h.has(unik.SORTED) and (np.diff(codes.astype(np.int64)) >= 0).all()
+            seen.append(codes)
+        if flag is None:
+            assert np.array_equal(np.sort(np.concatenate(seen)), np.sort(keys))
+        out = str(tmp_path / f"merged{flag or ''}")
+        run("merge", "-D", "-C", "-o", out, *extra, d)
+        h, codes, _ = unik.read_unik(out + ".unik")
+        assert np.array_equal(codes, exp), flag
+        assert h.has(unik.SORTED) and h.has(unik.CANONICAL) and h.number == 0
+        run("sort", "-C", "-o", out + "_mem", *extra, src)
+        assert np.array_equal(unik.read_unik(out + "_mem.unik")[1], exp)
+    # merge of explicit files, and the sorted-input check (merge.go:168-170)
+    run("merge", "-u", "-o", str(tmp_path / "m2"), os.path.join(str(tmp_path / "chunks"), "chunk_000.unik"),
+        os.path.join(str(tmp_path / "chunks"), "chunk_001.unik"))
+    p = subprocess.run([CLI, "merge", "-o", str(tmp_path / "bad"), src], capture_output=True, text=True)
+    assert p.returncode != 0 and "sorted" in p.stderr
+
+
 def test_single_file_is_a_byte_copy(c1):
     d, A, B = c1
     run("union", "-C", "-o", str(d / "copy"), str(d / "A.unik"))

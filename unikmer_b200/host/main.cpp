@@ -11,6 +11,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <ctype.h>
+#include <dirent.h>
+#include <errno.h>
+#include <sys/stat.h>
 
 #include <algorithm>
 #include <fstream>
@@ -51,6 +55,10 @@ struct Options {  // root.go:98-111 persistent flags
     bool canonical = false, hashed = false, sorted = false, circular = false, unique = false, repeated = false;
     uint32_t scale = 1, taxid = 0;
     int minimizer_w = 0;  // count -W
+    size_t chunk_size = 0;  // sort / split -m (k-mers per chunk; util.go:291 ParseByteSize)
+    std::string out_dir;    // split -O
+    bool is_dir = false;    // merge -D
+    bool force = false;     // split --force
     bool mix_taxid = false, compare_taxid = false;
     int number = 0;
     double proportion = 1.0;
@@ -66,6 +74,28 @@ void logi(const Options& o, const char* fmt, ...) {
     vfprintf(stderr, fmt, ap);
     fprintf(stderr, "\n");
     va_end(ap);
+}
+
+// util.go:291-335 ParseByteSize: a number with an optional B/K/M/G suffix (powers of 1024)
+size_t parse_byte_size(const char* v) {
+    std::string val(v);
+    while (!val.empty() && isspace((unsigned char)val.back())) val.pop_back();
+    if (val.empty()) return 0;
+    double unit = 1;
+    bool has_unit = true;
+    switch (val.back()) {
+        case 'B': case 'b': unit = 1; break;
+        case 'K': case 'k': unit = 1024.0; break;
+        case 'M': case 'm': unit = 1024.0 * 1024.0; break;
+        case 'G': case 'g': unit = 1024.0 * 1024.0 * 1024.0; break;
+        default: has_unit = false;
+    }
+    if (has_unit) val.pop_back();
+    if (val.empty()) return 0;
+    char* end = nullptr;
+    const double x = strtod(val.c_str(), &end);
+    if (end == val.c_str() || *end) die("invalid byte size: %s", v);
+    return x < 0 ? 0 : (size_t)(x * unit);
 }
 
 // ---- argument parsing: short/long flags of the six commands ------------------------------------------
@@ -98,7 +128,7 @@ Options parse(int argc, char** argv, int first) {
         else if (a == "--circular") o.circular = true;
         else if (a == "-u" || a == "--unique") o.unique = true;
         else if (a == "-d" || a == "--repeated") o.repeated = true;
-        else if (a == "-D" || a == "--scale") o.scale = (uint32_t)strtoul(need(i), nullptr, 10);
+        else if ((a == "-D" && std::string(argv[1]) != "merge") || a == "--scale") o.scale = (uint32_t)strtoul(need(i), nullptr, 10);
         else if (a == "-W" || a == "--minimizer-w") o.minimizer_w = atoi(need(i));
         else if (a == "-S" || a == "--syncmer-s") die("count -S (closed syncmers) is not supported by this build: bio/sketches is not pinned by the reference tree");
         else if (a == "-t" || a == "--taxid" || a == "--compare-taxid" || a == "--show-taxid") {
@@ -107,7 +137,13 @@ Options parse(int argc, char** argv, int first) {
             if (cmd == "count") o.taxid = (uint32_t)strtoul(need(i), nullptr, 10);
             else if (cmd == "diff") o.compare_taxid = true;
             else o.show_taxid = true;
-        } else if (a == "-m" || a == "--mix-taxid") o.mix_taxid = true;
+        } else if (a == "-m" && (std::string(argv[1]) == "sort" || std::string(argv[1]) == "split")) o.chunk_size = parse_byte_size(need(i));
+        else if (a == "--chunk-size") o.chunk_size = parse_byte_size(need(i));
+        else if (a == "-O" || a == "--out-dir") o.out_dir = need(i);
+        else if (a == "--is-dir" || (a == "-D" && std::string(argv[1]) == "merge")) o.is_dir = true;
+        else if (a == "--force") o.force = true;
+        else if (a == "-M" || a == "--max-open-files") (void)need(i);  // merge: no open-file limit on the device path
+        else if (a == "-m" || a == "--mix-taxid") o.mix_taxid = true;
         else if (a == "-n" || a == "--number") o.number = atoi(need(i));
         else if (a == "-p" || a == "--proportion") o.proportion = atof(need(i));
         else if (a == "-N" || a == "--show-code") o.show_code = true;
@@ -398,6 +434,117 @@ int cmd_sort(Options o) {  // sort.go:64-580 (in-memory path; -m chunks are a ho
     return 0;
 }
 
+// concatenated codes (+ taxids) of all inputs, unsorted: what sort / split accumulate before sorting (sort.go:226-239)
+void gather(const Inputs& in, bool tax, std::vector<uint64_t>& keys, std::vector<uint32_t>& tx) {
+    size_t total = 0;
+    for (auto& f : in.files) total += f.codes.size();
+    keys.reserve(total);
+    for (auto& f : in.files) {
+        keys.insert(keys.end(), f.codes.begin(), f.codes.end());
+        if (tax) {
+            if (f.taxids.size() == f.codes.size()) tx.insert(tx.end(), f.taxids.begin(), f.taxids.end());
+            else tx.insert(tx.end(), f.codes.size(), 0u);
+        }
+    }
+}
+
+// split (split.go:56-410): stage 1 of the external sort as a command -- chunks of -m k-mers, each sorted on the device
+// and written with the chunk fold of dumpCodes2File / dumpCodesTaxids2File (util-sort.go:35-190) to <out-dir>/chunk_NNN.unik.
+// (The reference's last chunk skips the taxid sort, quirk B-11; here every chunk is sorted.)
+int cmd_split(Options o) {
+    if (o.unique && o.repeated) die("flag -u/--unique overides -d/--repeated");
+    Inputs in = load_inputs(o, false, false, false);
+    std::string dir = o.out_dir.empty() ? (o.files[0] == "-" ? std::string("stdin.split") : o.files[0] + ".split") : o.out_dir;  // split.go:98-103
+    if (mkdir(dir.c_str(), 0777) != 0 && errno != EEXIST) die("cannot create %s", dir.c_str());
+    ukm_ctx* ctx = open_ctx(o);
+    const bool tax = in.has_taxid;
+    if (tax && (o.unique || o.repeated)) load_taxonomy(o, ctx);
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> tx;
+    gather(in, tax, keys, tx);
+    const size_t total = keys.size();
+    const size_t chunk = o.chunk_size ? o.chunk_size : (total ? total : 1);
+    const int key_bits = in.hashed ? 64 : 2 * in.k;
+    const int fold = o.unique ? UKM_FOLD_UNIQUE : (o.repeated ? UKM_FOLD_REPEATED_CHUNK : UKM_FOLD_PLAIN);
+    const uint32_t mode = base_mode(in, true, tax);
+    size_t n_chunks = 0, n_saved = 0;
+    for (size_t off = 0; off < total || (total == 0 && n_chunks == 0); off += chunk) {
+        const size_t m = std::min(chunk, total - off);
+        uint64_t* k = keys.data() + off;
+        uint32_t* t = tax ? tx.data() + off : nullptr;
+        if (m > 1) {
+            if (tax) CHECK(ctx, ukm_sort_pairs(ctx, k, t, m, key_bits, UKM_HOST));
+            else CHECK(ctx, ukm_sort_u64(ctx, k, m, key_bits, UKM_HOST));
+        }
+        char name[64];
+        snprintf(name, sizeof name, "/chunk_%03zu.unik", n_chunks);  // util-sort.go:192-194
+        Options oc = o;
+        oc.out = dir + name;
+        if (fold == UKM_FOLD_PLAIN) {
+            write_result(oc, in.k, mode, tax ? m : 0, o.max_taxid, k, t, m);  // Number: util-sort.go:181 (taxid chunks only)
+            n_saved += m;
+        } else {
+            ukm_span s;
+            memset(&s, 0, sizeof s);
+            s.keys = k;
+            s.taxids = t;
+            s.n = s.cap = m;
+            s.where = UKM_HOST;
+            s.sorted = 1;
+            Result r(m + 2, tax);
+            CHECK(ctx, ukm_fold_sorted(ctx, fold, &s, tax ? UKM_F_TAXID : 0, &r.span));
+            write_result(oc, in.k, mode, 0, o.max_taxid, r.codes.data(), tax ? r.taxids.data() : nullptr, r.n());
+            n_saved += r.n();
+        }
+        ++n_chunks;
+        if (total == 0) break;
+    }
+    logi(o, "%zu chunk files with total %zu k-mers saved to dir: %s", n_chunks, n_saved, dir.c_str());
+    ukm_destroy(ctx);
+    return 0;
+}
+
+// merge (merge.go:53-335): k-way merge of sorted chunk files with the plain / -u / -d folds of the FINAL round of
+// mergeChunksFile (util-sort.go:227-606).  -D: the arguments are directories holding chunk_NNN.unik files (merge.go:78-132).
+int cmd_merge(Options o) {
+    if (o.unique && o.repeated) die("flag -u/--unique overides -d/--repeated");
+    if (o.is_dir) {
+        std::vector<std::string> files;
+        for (auto& d : o.files) {
+            DIR* dh = opendir(d.c_str());
+            if (!dh) die("cannot read directory %s", d.c_str());
+            std::vector<std::string> found;
+            while (dirent* e = readdir(dh)) {
+                const std::string n = e->d_name;  // default pattern ^chunk_\d+\.unik$ (merge.go:344)
+                if (n.size() > 11 && n.compare(0, 6, "chunk_") == 0 && n.compare(n.size() - 5, 5, ".unik") == 0 &&
+                    n.find_first_not_of("0123456789", 6) == n.size() - 5)
+                    found.push_back(d + "/" + n);
+            }
+            closedir(dh);
+            std::sort(found.begin(), found.end());
+            files.insert(files.end(), found.begin(), found.end());
+        }
+        if (files.empty()) {
+            fprintf(stderr, "[WARN] no valid chunk files given\n");
+            return 0;
+        }
+        o.files = files;
+    }
+    Inputs in = load_inputs(o, true, false, true);  // merge.go:168-170: input files should be sorted
+    ukm_ctx* ctx = open_ctx(o);
+    const bool tax = in.has_taxid;
+    if (tax) load_taxonomy(o, ctx);  // merge.go:196-201
+    std::vector<ukm_span> sp = spans_of(in, tax);
+    size_t total = 0;
+    for (auto& s : sp) total += s.n;
+    const int fold = o.unique ? UKM_FOLD_UNIQUE : (o.repeated ? UKM_FOLD_REPEATED_FINAL : UKM_FOLD_PLAIN);
+    Result r(total + 2, tax);
+    CHECK(ctx, ukm_merge_sorted(ctx, fold, sp.data(), (int)sp.size(), tax ? UKM_F_TAXID : 0, &r.span));
+    write_result(o, in.k, base_mode(in, true, tax), 0, o.max_taxid, r.codes.data(), tax ? r.taxids.data() : nullptr, r.n());  // Number unset
+    ukm_destroy(ctx);
+    return 0;
+}
+
 int cmd_union(Options o) {  // union.go:53-312
     if (o.files.size() == 1) { copy_single(o); return 0; }
     Inputs in = load_inputs(o, false, false, true);
@@ -551,10 +698,10 @@ int main(int argc, char** argv) {
     if (argc < 2 || !strcmp(argv[1], "-h") || !strcmp(argv[1], "--help")) {
         fprintf(stderr,
                 "unikmer-b200: k-mer set operations on B200 (libukm)\n\n"
-                "usage: unikmer-b200 <count|sort|union|inter|diff|common|view|info> [flags] [files]\n"
+                "usage: unikmer-b200 <count|sort|union|inter|diff|common|split|merge|view|info> [flags] [files]\n"
                 "flags follow unikmer: -o, -C, -c, -i, -I, --max-taxid, --data-dir, --verbose, --device;\n"
                 "  count: -k -K -H -s --circular -D -W -t   sort: -u -d   union: -s   inter: -m\n"
-                "  diff: -s -t   common: -n -p -m   view: -t -N\n");
+                "  diff: -s -t   common: -n -p -m   split: -O -m -u -d   merge: -D -u -d   view: -t -N\n");
         return argc < 2 ? 1 : 0;
     }
     const std::string cmd = argv[1];
@@ -566,6 +713,8 @@ int main(int argc, char** argv) {
         if (cmd == "inter") return cmd_inter(o);
         if (cmd == "diff") return cmd_diff(o);
         if (cmd == "common") return cmd_common(o);
+        if (cmd == "split") return cmd_split(o);
+        if (cmd == "merge") return cmd_merge(o);
         if (cmd == "view") return cmd_view(o);
         if (cmd == "info") return cmd_info(o);
         die("unknown command: %s", cmd.c_str());
