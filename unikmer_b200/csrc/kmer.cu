@@ -664,9 +664,8 @@ extern "C" int ukm_count_seq(ukm_ctx* ctx, const uint8_t* bases, const uint64_t*
         // per-pass buffers: 1.3x the expected share, retried with twice the passes when a range still overflows
         size_t cap = small ? (size_t)P.total : (size_t)((double)P.total * sample_frac / (double)passes * 1.3) + (1u << 20);
         if (cap > P.total) cap = (size_t)P.total;
-        uint64_t *d_codes = nullptr, *d_uniq = nullptr;
+        uint64_t *d_codes = nullptr, *d_uniq = nullptr;  // d_uniq: staging of a pass's distinct codes, only when they cannot be folded in place
         UKM_TRY(tmp.alloc(&d_codes, cap + 2));
-        UKM_TRY(tmp.alloc(&d_uniq, cap + 2));
         size_t written = 0;
         bool overflow = false;
         uint64_t lo = 0;
@@ -689,20 +688,26 @@ extern "C" int ukm_count_seq(ukm_ctx* ctx, const uint8_t* bases, const uint64_t*
             if (kept) {
                 UKM_TRY(ukm_dev_sort(ctx, d_codes, nullptr, kept, key_bits));
                 size_t m = 0;
-                UKM_TRY(ukm_dev_fold(ctx, UKM_FOLD_UNIQUE, d_codes, nullptr, kept, false, d_uniq, nullptr, &m));
-                if (written + m > out->cap) {
-                    out->n = written + m;
-                    return ukm_fail(ctx, UKM_E_CAPACITY, "ukm_count_seq: output needs more than %zu elements", out->cap);
+                if (out_dev && written + kept <= out->cap) {
+                    // a device result is folded straight into place (no staging copy of the pass's 20 GB)
+                    UKM_TRY(ukm_dev_fold(ctx, UKM_FOLD_UNIQUE, d_codes, nullptr, kept, false, out->keys + written, nullptr, &m));
+                } else {
+                    if (!d_uniq) UKM_TRY(tmp.alloc(&d_uniq, cap + 2));
+                    UKM_TRY(ukm_dev_fold(ctx, UKM_FOLD_UNIQUE, d_codes, nullptr, kept, false, d_uniq, nullptr, &m));
+                    if (written + m > out->cap) {
+                        out->n = written + m;
+                        return ukm_fail(ctx, UKM_E_CAPACITY, "ukm_count_seq: output needs more than %zu elements", out->cap);
+                    }
+                    if (m) UKM_CUDA(ctx, cudaMemcpyAsync(out->keys + written, d_uniq, m * sizeof(uint64_t), kind, ctx->stream));
+                    UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
                 }
-                if (m) UKM_CUDA(ctx, cudaMemcpyAsync(out->keys + written, d_uniq, m * sizeof(uint64_t), kind, ctx->stream));
-                UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
                 written += m;
             }
             if (hi == top) break;
             lo = hi + 1;
         }
         tmp.free_now(d_codes);
-        tmp.free_now(d_uniq);
+        if (d_uniq) tmp.free_now(d_uniq);
         if (!overflow) {
             UKM_TRY(ukm_check_dev_error(ctx, "ukm_count_seq"));
             out->n = written;
