@@ -108,7 +108,9 @@ for rep, title in (("nway_union_prof", "nway_kernel<UNION> (one 8-way union of t
                    ("nway_filter_prof", "nway_kernel<INTER> (opt-in N-way hash filter, 4e9 k-mers in)"),
                    ("setop_pipe_prof", "setop_pipe_kernel (first two-way passes of inter / diff)"),
                    ("setop_search_prof", "setop_search_kernel (a later pass of inter: running set looked up in the next file)"),
-                   ("setop_union_prof", "setop_pipe_kernel (union passes, 1e9 k-mers in)"), ("onesweep_prof", "onesweep_kernel (one 8-bit pass over 3e8 keys)")):
+                   ("setop_union_prof", "setop_pipe_kernel (union passes, 1e9 k-mers in)"), ("onesweep_prof", "onesweep_kernel (one 8-bit pass over 3e8 keys)"),
+                   ("kmer_prof", "kmer_kernel<HASHED> (ntHash k=31 canonical over 3e8 bases: iterator, then the filtered variant of count)"),
+                   ("fold_prof", "fold_kernel<UNIQUE> (2.5e8 sorted keys)"), ("minimizer_prof", "minimizer_kernel (w=15 over 3e8 hashes)")):
     path = os.path.join(OUT, rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
