@@ -11,9 +11,9 @@
 namespace {
 
 constexpr int FD_THREADS = 256;
-constexpr int FD_ITEMS = 12;  // 3072 keys per tile: fewer look-back hand-offs than 8 (ncu: 55 % of the stalls were the barrier behind the look-back)
+constexpr int FD_ITEMS = 8;
 constexpr int FD_TILE = FD_THREADS * FD_ITEMS;
-#define FD_P(q) ((q) + (((q) + FD_ITEMS - 1) / FD_ITEMS))  // slot of halo-relative index q (q = element index + 1); a thread's FD_ITEMS keys are consecutive
+#define FD_P(q) ((q) + (((q) + 7) >> 3))  // slot of halo-relative index q (q = element index + 1); FD_P(8t+1 .. 8t+8) are consecutive
 
 template <int MODE, bool TAX>
 __global__ void __launch_bounds__(FD_THREADS)
@@ -21,11 +21,11 @@ __global__ void __launch_bounds__(FD_THREADS)
                 uint32_t* __restrict__ outT, uint64_t* __restrict__ status, uint32_t* __restrict__ tile_counter,
                 unsigned long long* __restrict__ total_out, int num_tiles, TaxDev tax, int* __restrict__ err) {
     constexpr int NW = FD_THREADS / 32;
-    // tile element i lives at s_k[FD_P(i + 1)]: one pad slot per FD_ITEMS elements, so that the blocked walk (thread t owns
-    // FD_ITEMS consecutive elements) strides an odd number of slots across a warp and every 8-byte access hits its own bank pair (the unpadded
+    // tile element i lives at s_k[FD_P(i + 1)]: one pad slot per 8 elements, so that the blocked walk (thread t owns
+    // elements 8t .. 8t+7) strides 9 slots across a warp and every 8-byte access hits its own bank pair (the unpadded
     // layout was an 8-way conflict on each of the three loads per key: half of the kernel's time)
-    __shared__ uint64_t s_k[FD_TILE + FD_TILE / FD_ITEMS + 4];  // FD_P(0) = left halo, FD_P(1..TILE) tile, FD_P(TILE+1) right halo
-    uint64_t* const s_ok = s_k;                // staging IN PLACE (the keys are in registers by then): a tile emits at most valid+1
+    __shared__ uint64_t s_k[FD_TILE + FD_TILE / 8 + 4];  // FD_P(0) = left halo, FD_P(1..TILE) tile, FD_P(TILE+1) right halo
+    __shared__ uint64_t s_ok[FD_TILE + 2];     // staging: a tile emits at most valid+1 (a run emitting 2 has >= 2 elements)
     __shared__ uint32_t s_ot[TAX ? FD_TILE + 2 : 1];
     __shared__ unsigned s_scan[NW + 2];
     __shared__ int s_tile;
@@ -51,17 +51,14 @@ __global__ void __launch_bounds__(FD_THREADS)
     // blocked walk: thread owns elements [tid*ITEMS, tid*ITEMS+ITEMS)
     unsigned emit2 = 0;  // 2 bits per item: number of copies to emit (0,1,2)
     uint32_t lca[FD_ITEMS];
-    uint64_t kreg[FD_ITEMS];
     unsigned cnt = 0;
 #pragma unroll
     for (int j = 0; j < FD_ITEMS; ++j) {
         const int i = tid * FD_ITEMS + j;
         unsigned e = 0;
         lca[j] = 0;
-        kreg[j] = 0;
         if (i < valid) {
             const uint64_t k = s_k[FD_P(1 + i)];
-            kreg[j] = k;
             const bool head = (i > 0 || has_left) ? (s_k[FD_P(i)] != k) : true;
             const bool next_same = (i + 1 < valid || has_right) ? (s_k[FD_P(2 + i)] == k) : false;
             if (head) {
@@ -90,7 +87,7 @@ __global__ void __launch_bounds__(FD_THREADS)
         for (int j = 0; j < FD_ITEMS; ++j) {
             const unsigned e = (emit2 >> (2 * j)) & 3u;
             if (e) {
-                const uint64_t k = kreg[j];
+                const uint64_t k = s_k[FD_P(1 + tid * FD_ITEMS + j)];
                 s_ok[o] = k;
                 if (TAX) s_ot[o] = lca[j];
                 ++o;

@@ -90,7 +90,7 @@ constexpr int KM_STAGE = 256;  // per-warp staging ring of the FILTER mode (flus
 // one 16-byte seed load per incoming and per outgoing base, codes stored in aligned pairs.
 template <bool HASHED, bool FILTER>
 __global__ void __launch_bounds__(KM_THREADS) kmer_kernel(const KmerArgs p) {
-    __shared__ __align__(16) uint8_t s_b[KM_TILE + KM_HALO + 16];  // class of every staged base
+    __shared__ uint8_t s_b[KM_TILE + KM_HALO + 16];  // class of every staged base
     __shared__ uint8_t s_lut[256];
     __shared__ uint64_t s_seed[4][8];  // [f_in, f_out(rol k), r_in(rol k-1), r_out(ror 1)][class 0..3, 4..7 = 0]
     __shared__ ulonglong2 s_in[8], s_out[8];  // {f_in, r_in}[class], {f_out, r_out}[class]: one load per base
@@ -116,23 +116,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmer_kernel(const KmerArgs p) {
         s_seed[t][c] = v;
     }
     __syncthreads();
-    {
-        // 16 bases per load where the source is 16-byte aligned (B0 is a multiple of 16: every tile of a cudaMalloc'd buffer)
-        const uint8_t* src = p.bases + B0;
-        const int nvec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) ? tile_len / 16 : 0;
-        const uint4* src4 = reinterpret_cast<const uint4*>(src);
-        for (int v = tid; v < nvec; v += KM_THREADS) {
-            const uint4 q = __ldg(src4 + v);
-            const unsigned w[4] = {q.x, q.y, q.z, q.w};
-            unsigned o[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                o[c] = (unsigned)s_lut[w[c] & 0xffu] | ((unsigned)s_lut[(w[c] >> 8) & 0xffu] << 8) |
-                       ((unsigned)s_lut[(w[c] >> 16) & 0xffu] << 16) | ((unsigned)s_lut[w[c] >> 24] << 24);
-            *reinterpret_cast<uint4*>(s_b + 16 * v) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        for (int i = 16 * nvec + tid; i < tile_len; i += KM_THREADS) s_b[i] = s_lut[src[i]];
-    }
+    for (int i = tid; i < tile_len; i += KM_THREADS) s_b[i] = s_lut[p.bases[B0 + i]];
     if (HASHED && tid < 8) {
         s_in[tid] = make_ulonglong2(s_seed[0][tid], s_seed[2][tid]);
         s_out[tid] = make_ulonglong2(s_seed[1][tid], s_seed[3][tid]);
