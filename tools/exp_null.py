@@ -1,0 +1,21 @@
+import os, sys, json, torch
+sys.path.insert(0, os.getcwd())
+from tools.exp_nway import timed
+from unikmer_b200 import Engine
+eng = Engine(0); stream = torch.cuda.Stream(); eng.use_stream(stream.cuda_stream)
+with torch.cuda.stream(stream):
+    U = 10**9
+    files = [eng.synth_member_file(0, U, U, 3, 4, f).clone() for f in range(8)]
+    out = torch.empty(int(files[0].shape[0]) + 16, dtype=torch.int64, device="cuda")
+    os.environ["UKM_NWAY_FILTER"] = "1"
+    for null in ("1", "0"):
+        os.environ["UKM_NWAY_NULL"] = null
+        for cfg in ("0", "4", "2"):
+            os.environ["UKM_NWAY_CFG"] = cfg
+            for name, fn in (("inter", eng.inter), ("diff", eng.diff)):
+                eng.stats_reset(); eng.stats_enable(True)
+                ms = timed(stream, lambda: fn(files, out=out), reps=3)
+                eng.stats_enable(False)
+                st = eng.stats()
+                print(json.dumps({"null": null, "cfg": cfg, "op": name, "ms": round(ms, 3), "n_out": int(fn(files, out=out)[0].shape[0]),
+                                  "k": {k: round(v["ms"] / max(v["launches"], 1), 3) for k, v in st.items()}}), flush=True)

@@ -92,6 +92,7 @@ struct NwArgs {
     uint64_t* status;  // one count word per tile (flag << 62 | count)
     unsigned long long* total_out;
     int num_tiles;
+    int null_mode;  // UKM_NWAY_NULL=1: inter / diff tiles do no work (measures the tile machinery alone)
     int* err;
 };
 
@@ -111,117 +112,97 @@ struct NwShape {
 };
 
 // ---- inter / diff of one tile: which of file 0's keys occur in the other files -----------------------------
-// The tile's file-0 keys go into an open-addressing table in shared memory (64-bit keys, linear probing, at most
-// half full); every key of every other file is looked up once and, on a hit, sets its file's bit in the byte that
-// belongs to the table slot.  A file-0 key survives `inter` when all bits are set, `diff` when none is.  That is
-// inter.go:205-267 / diff.go:380-435 for all files at once: a two-pointer walk per file costs a shared-memory
-// load per element per file, this costs about one probe per element.  Tiles whose file-0 share does not fit the
-// table (or that hold both key 0 and key 2^64-1, leaving no value for "empty") mark hits by binary search instead.
-constexpr int NWF_TABN = 2048;  // table slots
-constexpr int NWF_EPT = 4;      // file-0 keys per thread on the table path
+// File 0's keys of the tile are the candidates; they are looked up (branch-free binary search in shared memory) in
+// the other files' segments.  The first NWF_SEQ files run one after the other over a shrinking work list -- after
+// each file only the survivors stay (inter: found, diff: not found), which is inter.go:205-286 / diff.go:380-435
+// with its early exit, on a tile -- and the remaining files are probed together, one (candidate, file) pair per
+// thread, clearing the candidate's flag.  Work lists are unordered (a shared counter hands out slots); the flags
+// are per position in file 0's segment, so the final compaction restores key order.
+// (An earlier version hashed file 0's keys and probed every key of every other file: 133 instructions per key,
+// 28-34 ms per C3 operation -- DESIGN.md 4.3.)
+constexpr int NWF_SEQ = 3;
 
-__device__ __forceinline__ unsigned nwf_hash(uint64_t x) {
-    return (unsigned)((x * 0x9E3779B97F4A7C15ull) >> 53);  // top 11 bits of the Fibonacci product: [0, 2048)
+__device__ __forceinline__ bool nwf_contains(const uint64_t* seg, int n, uint64_t x) {
+    int pos = 0;  // lower_bound of x; the answer lies in [pos, pos + n]
+    int m = n;
+    while (m > 1) {
+        const int half = m >> 1;
+        if (seg[pos + half] < x) pos += half;
+        m -= half;
+    }
+    if (m == 1 && seg[pos] < x) ++pos;
+    return pos < n && seg[pos] == x;
 }
 
 template <int OP, int NT, int VT>
-__device__ __forceinline__ unsigned nw_filter_tile(const uint64_t* slot, const NwGeom<NW_MAX>& g, uint64_t* tab, uint32_t* m32,
-                                                   int tid, int nf, uint64_t* outk) {
+__device__ __forceinline__ unsigned nw_filter_tile(const uint64_t* slot, const NwGeom<NW_MAX>& g, uint64_t* xreg, int* s_cnt3, int tid,
+                                                   int nf, bool null_mode, uint64_t* outk) {
     constexpr int CAP = NwShape<NW_MAX, NT, VT>::CAP;
-    constexpr int MW = ((CAP > NWF_TABN ? CAP : NWF_TABN) + 3) / 4;  // one byte per table slot / per file-0 position
-    const unsigned lane = lane_id();
+    uint8_t* alive = reinterpret_cast<uint8_t*>(xreg);                                 // CAP bytes (+ padding)
+    uint16_t* list0 = reinterpret_cast<uint16_t*>(xreg + (CAP + 7) / 8 + 1);            // CAP entries each
+    uint16_t* list1 = list0 + ((CAP + 3) & ~3);
     const int n0 = g.n[0];
     const uint64_t* seg0 = slot + g.off[0];
-    const int ept = (n0 + NT - 1) / NT;  // file-0 keys per thread, blocked: thread t owns [t*ept, (t+1)*ept)
-    const uint64_t lo0 = n0 ? seg0[0] : 1, hi0 = n0 ? seg0[n0 - 1] : 1;
-    const uint64_t EMPTY = lo0 > 0 ? lo0 - 1 : hi0 + 1;  // a value no file-0 key of this tile has
-    const bool hashed = (lo0 > 0 || hi0 != ~0ull) && n0 <= NWF_TABN / 2 && ept <= NWF_EPT;
-    // A: clear
-    if (hashed)
-        for (int j = tid; j < NWF_TABN; j += NT) tab[j] = EMPTY;
-    for (int j = tid; j < MW; j += NT) m32[j] = 0;
-    named_bar_sync(1, NT);
-    // B: my file-0 keys (kept in registers; on the table path also inserted)
-    int hs[NWF_EPT];
-#pragma unroll
-    for (int r = 0; r < NWF_EPT; ++r) hs[r] = 0;
-#pragma unroll
-    for (int r = 0; r < VT; ++r) {
-        const int i0 = tid * ept + r;
-        outk[r] = 0;
-        if (r < ept && i0 < n0) {
-            const uint64_t x = seg0[i0];
-            outk[r] = x;
-            if (r < NWF_EPT && hashed) {
-                unsigned h = nwf_hash(x);
-                for (int pr = 0; pr < NWF_TABN; ++pr) {
-                    const unsigned long long old =
-                        atomicCAS(reinterpret_cast<unsigned long long*>(&tab[h]), (unsigned long long)EMPTY, (unsigned long long)x);
-                    if (old == EMPTY || old == x) break;
-                    h = (h + 1) & (NWF_TABN - 1);
-                }
-                hs[r] = (int)h;
-            }
-        }
-    }
-    named_bar_sync(1, NT);
-    // C: every key of files 1..nf-1, in chunks of 32 handed to the warps round robin
-    {
-        const int nfl = (lane >= 1 && (int)lane < nf) ? g.n[lane] : 0;
-        const int ch = (nfl + 31) >> 5;
-        const int incl = (int)warp_incl_scan_u32((unsigned)ch);
-        const int total_ch = __shfl_sync(0xffffffffu, incl, 31);
-        for (int c = tid >> 5; c < total_ch; c += NT / 32) {
-            const int f = __popc(__ballot_sync(0xffffffffu, incl <= c));  // first file whose chunks reach past c
-            const int excl_f = __shfl_sync(0xffffffffu, incl - ch, f);
-            const int n_f = __shfl_sync(0xffffffffu, nfl, f);
-            const int i = (c - excl_f) * 32 + (int)lane;
-            if (i < n_f) {
-                const uint64_t y = slot[g.off[f] + i];
-                int hit = -1;
-                if (hashed) {
-                    unsigned h = nwf_hash(y);
-                    for (int pr = 0; pr < NWF_TABN; ++pr) {
-                        const uint64_t k = tab[h];
-                        if (k == EMPTY) break;
-                        if (k == y) { hit = (int)h; break; }
-                        h = (h + 1) & (NWF_TABN - 1);
-                    }
-                } else {
-                    int pos = 0, n = n0;  // lower_bound of y in file 0's keys; the answer lies in [pos, pos + n]
-                    while (n > 1) {
-                        const int half = n >> 1;
-                        if (seg0[pos + half] < y) pos += half;
-                        n -= half;
-                    }
-                    if (n == 1 && seg0[pos] < y) ++pos;
-                    if (pos < n0 && seg0[pos] == y) hit = pos;
-                }
-                if (hit >= 0) atomicOr(&m32[hit >> 2], (1u << f) << ((hit & 3) * 8));
-            }
-        }
-    }
-    named_bar_sync(1, NT);
-    // D: verdict per file-0 key
-    const unsigned full = ((1u << nf) - 1u) & ~1u;
+    const int ept = (n0 + NT - 1) / NT;  // file-0 keys per thread in the ordered pass: thread t owns [t*ept, (t+1)*ept)
     unsigned mask = 0;
 #pragma unroll
+    for (int r = 0; r < VT; ++r) outk[r] = 0;
+    if (null_mode) return 0;  // measurement aid: the tile machinery without any work
+    const int nsub = nf - 1;
+    const int nseq = nsub < NWF_SEQ ? nsub : NWF_SEQ;
+    // flags start at 0; the survivors of the sequential rounds set theirs
+    for (int j = tid; j < (n0 + 3) / 4; j += NT) reinterpret_cast<uint32_t*>(alive)[j] = 0;
+    if (tid < 3) s_cnt3[tid] = 0;
+    named_bar_sync(1, NT);
+    // sequential rounds over files 1 .. nseq: list (round - 1) -> list (round)
+    int cnt_in = n0;
+    for (int f = 1; f <= nseq; ++f) {
+        const uint16_t* lin = (f & 1) ? list1 : list0;  // round 1 reads the identity list (no array)
+        uint16_t* lout = (f & 1) ? list0 : list1;
+        const uint64_t* seg = slot + g.off[f];
+        const int nfseg = g.n[f];
+        int* c_out = &s_cnt3[f % 3];
+        for (int i = tid; i < cnt_in; i += NT) {
+            const int idx = f == 1 ? i : (int)lin[i];
+            const uint64_t x = seg0[idx];
+            const bool found = nwf_contains(seg, nfseg, x);
+            if (OP == NWOP_INTER ? found : !found) lout[atomicAdd(c_out, 1)] = (uint16_t)idx;
+        }
+        if (tid == 0) s_cnt3[(f + 1) % 3] = 0;  // the counter of the round after next (nobody reads or adds to it now)
+        named_bar_sync(1, NT);
+        cnt_in = *c_out;
+    }
+    const uint16_t* lfin = (nseq & 1) ? list0 : list1;
+    for (int i = tid; i < cnt_in; i += NT) alive[nseq == 0 ? i : (int)lfin[i]] = 1;
+    named_bar_sync(1, NT);
+    // the remaining files together: one (survivor, file) pair per thread, a miss (inter) / a hit (diff) clears the flag
+    const int npar = nsub - nseq;
+    if (npar > 0) {
+        const int pairs = cnt_in * npar;
+        for (int q = tid; q < pairs; q += NT) {
+            const int i = q / npar, f = nseq + 1 + (q - i * npar);
+            const int idx = (int)lfin[i];
+            const bool found = nwf_contains(slot + g.off[f], g.n[f], seg0[idx]);
+            if (OP == NWOP_INTER ? !found : found) alive[idx] = 0;
+        }
+        named_bar_sync(1, NT);
+    }
+    // ordered pass: my file-0 positions, in key order
+#pragma unroll
     for (int r = 0; r < VT; ++r) {
         const int i0 = tid * ept + r;
-        if (r < ept && i0 < n0) {
-            const int idx = (hashed && r < NWF_EPT) ? hs[r < NWF_EPT ? r : 0] : i0;
-            const unsigned m = (m32[idx >> 2] >> ((idx & 3) * 8)) & 0xffu;
-            const bool keep = OP == NWOP_INTER ? (m == full) : (m == 0);
-            mask |= (keep ? 1u : 0u) << r;
+        if (r < ept && i0 < n0 && alive[i0]) {
+            outk[r] = seg0[i0];
+            mask |= 1u << r;
         }
     }
     return mask;
 }
 
 template <int OP, int NWAY, int NT, int VT>
-constexpr int nw_x_elems() {  // the second shared-memory region: merge buffer X (union) or table + hit bytes (inter / diff)
+constexpr int nw_x_elems() {  // the second shared-memory region: merge buffer X (union) or flags + two work lists (inter / diff)
     using SH = NwShape<NWAY, NT, VT>;
-    return OP == NWOP_UNION ? SH::X_E : NWF_TABN + (((SH::CAP > NWF_TABN ? SH::CAP : NWF_TABN) + 3) / 4 + 1) / 2 + 2;
+    return OP == NWOP_UNION ? SH::X_E : (SH::CAP + 7) / 8 + 1 + 2 * (((SH::CAP + 3) & ~3) / 4) + 2;
 }
 
 template <int OP, int NWAY, int NT, int VT, int SLOTS, int MINB>
@@ -239,6 +220,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
     __shared__ NwGeom<NWAY> s_geom[SLOTS];
     __shared__ const uint64_t* s_fk[NW_MAX];
     __shared__ unsigned s_scan[NW + 2];
+    __shared__ int s_cnt3[4];  // rotating work-list counters of the inter / diff rounds
 
     const int G = gridDim.x;
     const int n_my = (p.num_tiles - (int)blockIdx.x + G - 1) / G;  // tiles of this CTA
@@ -385,7 +367,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
             }
             const NwGeom<NWAY>& g = s_geom[s];
             if constexpr (OP != NWOP_UNION) {
-                emitmask = nw_filter_tile<OP, NT, VT>(slot, g, s_x, reinterpret_cast<uint32_t*>(s_x + NWF_TABN), tid, p.F.nf, outk);
+                emitmask = nw_filter_tile<OP, NT, VT>(slot, g, s_x, s_cnt3, tid, p.F.nf, p.null_mode != 0, outk);
             } else {
             const uint64_t* src = slot;
             uint64_t* dst = s_x;
@@ -561,6 +543,10 @@ int nway_run(ukm_ctx* ctx, int op, const char* stat_name, const uint64_t* const*
     pa.total = total;
     a.outK = outK;
     a.err = ctx->d_err;
+    {
+        const char* e = getenv("UKM_NWAY_NULL");
+        a.null_mode = (e && e[0] == '1') ? 1 : 0;
+    }
     ukm_tmp tmp(ctx);
     {
         ukm_stat_scope st(ctx, stat_name, (double)total * 8.0);  // every input key read once (+ the output, added below)
