@@ -10,7 +10,7 @@ with torch.cuda.stream(stream):
     os.environ["UKM_NWAY_FILTER"] = "1"
     for null in ("1", "0"):
         os.environ["UKM_NWAY_NULL"] = null
-        for cfg in ("0", "4", "2"):
+        for cfg in ("0", "4", "2", "5", "6"):
             os.environ["UKM_NWAY_CFG"] = cfg
             for name, fn in (("inter", eng.inter), ("diff", eng.diff)):
                 eng.stats_reset(); eng.stats_enable(True)
@@ -19,3 +19,10 @@ with torch.cuda.stream(stream):
                 st = eng.stats()
                 print(json.dumps({"null": null, "cfg": cfg, "op": name, "ms": round(ms, 3), "n_out": int(fn(files, out=out)[0].shape[0]),
                                   "k": {k: round(v["ms"] / max(v["launches"], 1), 3) for k, v in st.items()}}), flush=True)
+    # the union through the same shapes
+    outu = torch.empty(min(sum(int(f.shape[0]) for f in files), U) + 16, dtype=torch.int64, device="cuda")
+    os.environ["UKM_NWAY_NULL"] = "0"
+    for cfg in ("0", "5", "6"):
+        os.environ["UKM_NWAY_CFG"] = cfg
+        ms = timed(stream, lambda: eng.union(files, out=outu), reps=3)
+        print(json.dumps({"op": "union", "cfg": cfg, "ms": round(ms, 3)}), flush=True)

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
     using SH = NwShape<NWAY, NT, VT>;
     static_assert(OP == NWOP_UNION || NWAY == NW_MAX, "inter / diff tiles are laid out for 8 files");
     constexpr int NW = NT / 32;
-    constexpr int DEFER = SLOTS - 2;
+    constexpr int DEFER = 1;  // copy-out lag in tiles; the loader runs SLOTS - 2 tiles ahead of the merging warps
     constexpr int LEVELS = SH::LEVELS;
     extern __shared__ __align__(16) unsigned char nw_smem[];
     uint64_t* s_slots = reinterpret_cast<uint64_t*>(nw_smem);  // SLOTS * SLOT_E
@@ -240,18 +240,23 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
     if (threadIdx.x < 32) {
         // ================= loader warp: lane f owns file f =================
         const uint64_t* fk = lane < NWAY ? s_fk[lane] : nullptr;
+        // the cut positions of a tile are fetched one tile ahead, so their (L2 / HBM) latency is not on the per-tile path
+        long long lo_nx = 0, hi_nx = 0;
+        if (lane < NWAY && n_my > 0) {
+            lo_nx = p.bounds[blockIdx.x].pos[lane];
+            hi_nx = p.bounds[blockIdx.x + 1].pos[lane];
+        }
         for (int li = 0; li < n_my; ++li) {
             const int s = li % SLOTS, u = li / SLOTS;
+            long long lo = lo_nx;
+            int n = (int)(hi_nx - lo_nx);
+            if (lane < NWAY && li + 1 < n_my) {
+                const int tnx = (int)blockIdx.x + (li + 1) * G;
+                lo_nx = p.bounds[tnx].pos[lane];
+                hi_nx = p.bounds[tnx + 1].pos[lane];
+            }
             if (u > 0 && !mbar_wait(&empty_bar[s], (unsigned)(u - 1) & 1u)) {
                 if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
-            }
-            const int tile = (int)blockIdx.x + li * G;
-            long long lo = 0;
-            int n = 0;
-            if (lane < NWAY) {
-                lo = p.bounds[tile].pos[lane];
-                const long long hi = p.bounds[tile + 1].pos[lane];
-                n = (int)(hi - lo);
             }
             int sum = n;
 #pragma unroll
@@ -510,7 +515,7 @@ int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_
 int nway_cfg() {
     const char* e = getenv("UKM_NWAY_CFG");
     const int v = e ? atoi(e) : 0;
-    return (v >= 0 && v < 5) ? v : 0;
+    return (v >= 0 && v < 7) ? v : 0;
 }
 
 template <int OP, int NWAY>
@@ -520,6 +525,8 @@ int launch_nway_cfg(ukm_ctx* ctx, const NwArgs& a, const NwPartArgs& pa, ukm_tmp
         case 2: return launch_nway<OP, NWAY, 512, 13, 3, 1>(ctx, a, pa, tmp, fell_back);
         case 3: return launch_nway<OP, NWAY, 128, 17, 4, 2>(ctx, a, pa, tmp, fell_back);
         case 4: return launch_nway<OP, NWAY, 256, 9, 3, 3>(ctx, a, pa, tmp, fell_back);
+        case 5: return launch_nway<OP, NWAY, 256, 9, 5, 2>(ctx, a, pa, tmp, fell_back);
+        case 6: return launch_nway<OP, NWAY, 256, 13, 4, 1>(ctx, a, pa, tmp, fell_back);
         default: return launch_nway<OP, NWAY, 256, 13, 3, 2>(ctx, a, pa, tmp, fell_back);
     }
 }
