@@ -515,7 +515,7 @@ int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_
 int nway_cfg() {
     const char* e = getenv("UKM_NWAY_CFG");
     const int v = e ? atoi(e) : 0;
-    return (v >= 0 && v < 7) ? v : 0;
+    return (v >= 0 && v < 5) ? v : 0;
 }
 
 template <int OP, int NWAY>
@@ -525,8 +525,6 @@ int launch_nway_cfg(ukm_ctx* ctx, const NwArgs& a, const NwPartArgs& pa, ukm_tmp
         case 2: return launch_nway<OP, NWAY, 512, 13, 3, 1>(ctx, a, pa, tmp, fell_back);
         case 3: return launch_nway<OP, NWAY, 128, 17, 4, 2>(ctx, a, pa, tmp, fell_back);
         case 4: return launch_nway<OP, NWAY, 256, 9, 3, 3>(ctx, a, pa, tmp, fell_back);
-        case 5: return launch_nway<OP, NWAY, 256, 9, 5, 2>(ctx, a, pa, tmp, fell_back);
-        case 6: return launch_nway<OP, NWAY, 256, 13, 4, 1>(ctx, a, pa, tmp, fell_back);
         default: return launch_nway<OP, NWAY, 256, 13, 3, 2>(ctx, a, pa, tmp, fell_back);
     }
 }

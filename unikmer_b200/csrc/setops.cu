@@ -1088,9 +1088,10 @@ bool nway_force() {
     const char* e = getenv("UKM_NWAY_FORCE");
     return e && e[0] == '1';
 }
-// The N-way inter / diff filter is correct but, measured on B200 (C3: 28.6-34 ms against 13.3 ms for the
-// file-by-file passes), slower: its five barrier-separated phases per tile are latency bound.  It stays
-// opt-in (UKM_NWAY_FILTER=1, or UKM_NWAY_FORCE=1) until that is fixed.
+// The N-way inter / diff filter is correct but, measured on B200 (C3: 23.3-24.3 ms against 12.7 ms for the
+// file-by-file passes), slower: with so little work per tile the kernel runs at the pace of the grid-wide
+// output-offset hand-off (16.8 ms with NO work per tile, UKM_NWAY_NULL=1).  It stays opt-in
+// (UKM_NWAY_FILTER=1, or UKM_NWAY_FORCE=1) until its outputs are decoupled from that hand-off.
 bool nway_filter_enabled() {
     const char* e = getenv("UKM_NWAY_FILTER");
     return (e && e[0] == '1') || nway_force();
