@@ -92,7 +92,7 @@ struct NwArgs {
     uint64_t* status;  // one count word per tile (flag << 62 | count)
     unsigned long long* total_out;
     int num_tiles;
-    int null_mode;  // UKM_NWAY_NULL=1: inter / diff tiles do no work (measures the tile machinery alone)
+    int null_mode;  // measurement aids for inter / diff (results are NOT valid): UKM_NWAY_NULL=1 tiles do no work, =2 load pipeline only
     int* err;
 };
 
@@ -205,12 +205,12 @@ constexpr int nw_x_elems() {  // the second shared-memory region: merge buffer X
     return OP == NWOP_UNION ? SH::X_E : (SH::CAP + 7) / 8 + 1 + 2 * (((SH::CAP + 3) & ~3) / 4) + 2;
 }
 
-template <int OP, int NWAY, int NT, int VT, int SLOTS, int MINB>
+template <int OP, int NWAY, int NT, int VT, int SLOTS, int MINB, int DEFER = 1>
 __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p) {
     using SH = NwShape<NWAY, NT, VT>;
     static_assert(OP == NWOP_UNION || NWAY == NW_MAX, "inter / diff tiles are laid out for 8 files");
     constexpr int NW = NT / 32;
-    constexpr int DEFER = 1;  // copy-out lag in tiles; the loader runs SLOTS - 2 tiles ahead of the merging warps
+    static_assert(DEFER >= 1 && DEFER <= SLOTS - 2, "copy-out lag in tiles; the loader runs SLOTS - DEFER - 1 tiles ahead");
     constexpr int LEVELS = SH::LEVELS;
     extern __shared__ __align__(16) unsigned char nw_smem[];
     uint64_t* s_slots = reinterpret_cast<uint64_t*>(nw_smem);  // SLOTS * SLOT_E
@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
     }
     if (threadIdx.x < 64) {
         // ================= prefix warp (same scheme as setop_pipe_kernel) =================
+        if (OP != NWOP_UNION && p.null_mode == 2) return;  // measurement aid: no output offsets at all
         constexpr int MAXM = NWK_MAX_GRID / 32;
         unsigned long long P = 0;  // outputs of all earlier grid iterations (identical on every CTA)
         for (int bi = 0; bi < n_my; ++bi) {
@@ -359,6 +360,18 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
 
     // ================= consumers =================
     const int tid = (int)threadIdx.x - NWK_AUX;
+    if (OP != NWOP_UNION && p.null_mode == 2) {
+        // measurement aid (UKM_NWAY_NULL=2): the load pipeline alone -- wait for a tile, hand its slot back
+        for (int i = 0; i < n_my; ++i) {
+            const int s = i % SLOTS, u = i / SLOTS;
+            if (!mbar_wait(&full_bar[s], (unsigned)u & 1u)) {
+                if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+            }
+            mbar_arrive(&empty_bar[s]);
+        }
+        if (tid == 0 && blockIdx.x == 0) *p.total_out = 0;
+        return;
+    }
     for (int i = 0; i < n_my + DEFER; ++i) {
         unsigned emitmask = 0;
         uint64_t outk[VT];
@@ -451,11 +464,11 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-template <int OP, int NWAY, int NT, int VT, int SLOTS, int MINB>
+template <int OP, int NWAY, int NT, int VT, int SLOTS, int MINB, int DEFER = 1>
 int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_back) {
     using SH = NwShape<NWAY, NT, VT>;
     constexpr size_t smem = ((size_t)SLOTS * SH::SLOT_E + nw_x_elems<OP, NWAY, NT, VT>()) * 8;
-    auto kern = nway_kernel<OP, NWAY, NT, VT, SLOTS, MINB>;
+    auto kern = nway_kernel<OP, NWAY, NT, VT, SLOTS, MINB, DEFER>;
     static int ctas_per_sm = 0;  // per instantiation
     if (ctas_per_sm == 0) {
         UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -550,7 +563,7 @@ int nway_run(ukm_ctx* ctx, int op, const char* stat_name, const uint64_t* const*
     a.err = ctx->d_err;
     {
         const char* e = getenv("UKM_NWAY_NULL");
-        a.null_mode = (e && e[0] == '1') ? 1 : 0;
+        a.null_mode = e ? atoi(e) : 0;
     }
     ukm_tmp tmp(ctx);
     {
