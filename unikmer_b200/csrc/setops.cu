@@ -170,6 +170,7 @@ struct SetopArgs {
     unsigned long long* total_out;
     int num_tiles;
     unsigned flags;      // UKM_F_MIX_TAXID | UKM_F_COMPARE_TAXID
+    int null_mode;       // measurement aid (UKM_SETOP_NULL=1, results NOT valid): the pipeline kernel skips search and walk
     uint32_t threshold;  // OP_UNION with counts: emit only (count & 0xffff) >= threshold (0 = all)
     TaxDev tax;
     int* err;
@@ -622,6 +623,7 @@ __global__ void __launch_bounds__(NT + PIPE_AUX, MINB) setop_pipe_kernel(const S
             const uint64_t* sA = slot + g.hA;
             const uint64_t* sB = slot + g.offB;
             const int total = na + nb;
+            if (!p.null_mode) {
             {
                 int diag = tid * VT;
                 if (diag > total) diag = total;
@@ -656,6 +658,7 @@ __global__ void __launch_bounds__(NT + PIPE_AUX, MINB) setop_pipe_kernel(const S
                 if (takeA) ka = *++qa;
                 if (takeB || (eq && OP != OP_MERGE)) kb = *++qb;
             }
+            }  // !null_mode
             unsigned tile_total;
             off = group_excl_scan_u32<NT>((unsigned)__popc(emitmask), (unsigned)tid, s_scan, &tile_total, 1);
             // every consumer is past its walk (two barriers inside the scan): the slot may be overwritten
@@ -968,6 +971,10 @@ int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, boo
     a.status = d_status; a.tile_counter = d_counter; a.total_out = d_total;
     a.num_tiles = num_tiles;
     a.flags = flags;
+    {
+        const char* e = getenv("UKM_SETOP_NULL");
+        a.null_mode = (e && e[0] == '1') ? 1 : 0;
+    }
     a.threshold = threshold;
     a.tax = ukm_taxdev(ctx);
     a.err = ctx->d_err;
