@@ -240,22 +240,14 @@ def main():
             # peer pulls run on the copy engines while the passes whose inputs have arrived run: per arriving pair of
             # files one union level-1 merge and the next two links of the inter / diff chains (the same passes, in the
             # same file order, as eng.inter(files) / eng.diff(files) / eng.union(files)); the upper union levels follow
-            # every rank pulls file 0 first and the rest in an order rotated by rank (all owners send at once); the set
-            # operations do not care about the order of files 1..7: inter and union are commutative, diff subtracts them all
-            order = pex.pull_order()
-            files, ev = pex.exchange_async(splitters, order=order)
-            lvl, ci, cd, pend = [], None, None, []
-            for f in order:
-                pex.wait(ev, (f,))
-                F = files[f]
-                ci = F if ci is None else (eng.inter([ci, F])[0] if ci.shape[0] else ci)
-                cd = F if f == 0 else (eng.diff([cd, F])[0] if cd.shape[0] else cd)
-                pend.append(F)
-                if len(pend) == 2:
-                    lvl.append(eng.union(pend)[0])
-                    pend = []
-            if pend:
-                lvl.append(pend[0])
+            files, ev = pex.exchange_async(splitters)
+            lvl, ci, cd = [], None, None
+            for q in range(0, N_FILES, 2):
+                pex.wait(ev, (q, q + 1))
+                pair = files[q:q + 2]
+                lvl.append(eng.union(pair)[0])
+                ci = eng.inter(pair if ci is None else [ci] + pair)[0] if (ci is None or ci.shape[0]) else ci
+                cd = eng.diff(pair if cd is None else [cd] + pair)[0] if (cd is None or cd.shape[0]) else cd
             while len(lvl) > 1:
                 lvl = [eng.union(lvl[q:q + 2])[0] for q in range(0, len(lvl), 2)]
             return ci, cd, lvl[0]

@@ -154,19 +154,9 @@ class PeerPullExchange:
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
         self.bufs: Dict[int, torch.Tensor] = {}
 
-    def pull_order(self) -> List[int]:
-        """Order in which this rank pulls (and consumes) the files: file 0 first (diff needs it before anything else), the
-        others rotated by rank, so that at any moment the ranks pull from DIFFERENT owners -- with every rank walking
-        0, 1, 2, ... only as many owners as there are copy streams would be sending at a time."""
-        rest = list(range(1, self.n_files))
-        if rest:
-            k = (self.rank * len(rest)) // max(self.world, 1)
-            rest = rest[k:] + rest[:k]
-        return [0] + rest if self.n_files else []
-
-    def exchange_async(self, splitters: np.ndarray, order=None):
+    def exchange_async(self, splitters: np.ndarray):
         """Returns (slices, events): slices[f] = this rank's key-range slice of file f; events[f] = CUDA event to wait
-        on before reading it (None for local views).  `order` = the order in which the pulls are issued."""
+        on before reading it (None for local views)."""
         G, me, n_files = self.world, self.rank, self.n_files
         # slice boundaries: the owner binary-searches its files; one small all-reduce shares them
         bounds = torch.zeros(n_files, G + 1, dtype=torch.int64)
@@ -180,7 +170,7 @@ class PeerPullExchange:
         ready.record(cur)
         slices: List[torch.Tensor] = [None] * n_files  # type: ignore
         events: List[torch.cuda.Event] = [None] * n_files  # type: ignore
-        for i, f in enumerate(order if order is not None else range(n_files)):
+        for i, f in enumerate(range(n_files)):
             lo, hi = int(bounds[f, me]), int(bounds[f, me + 1])
             if f in self.local:
                 slices[f] = self.local[f][lo:hi]
