@@ -1,3 +1,5 @@
+"""N-way inter / diff with and without per-tile work (UKM_NWAY_NULL=1: no work, =2: load pipeline only; results not valid).
+Needs a measurement build of the library:  make -C unikmer_b200/csrc clean all EXTRA=-DUKM_MEASURE"""
 import os, sys, json, torch
 sys.path.insert(0, os.getcwd())
 from tools.exp_nway import timed

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """The two-way pipeline kernel with and without its merge work (UKM_SETOP_NULL=1: load, scan, offset hand-off and
-copy-out only -- results are not valid) on one pass F0 x F1 of the C3 files: what the tile machinery alone costs."""
+copy-out only -- results are not valid) on one pass F0 x F1 of the C3 files: what the tile machinery alone costs.
+Needs a measurement build of the library:  make -C unikmer_b200/csrc clean all EXTRA=-DUKM_MEASURE"""
 import json
 import os
 import sys

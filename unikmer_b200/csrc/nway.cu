@@ -561,10 +561,13 @@ int nway_run(ukm_ctx* ctx, int op, const char* stat_name, const uint64_t* const*
     pa.total = total;
     a.outK = outK;
     a.err = ctx->d_err;
+    a.null_mode = 0;
+#ifdef UKM_MEASURE  // measurement build only (make EXTRA=-DUKM_MEASURE): the null modes produce no valid result
     {
         const char* e = getenv("UKM_NWAY_NULL");
         a.null_mode = e ? atoi(e) : 0;
     }
+#endif
     ukm_tmp tmp(ctx);
     {
         ukm_stat_scope st(ctx, stat_name, (double)total * 8.0);  // every input key read once (+ the output, added below)

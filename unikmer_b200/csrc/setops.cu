@@ -971,10 +971,13 @@ int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, boo
     a.status = d_status; a.tile_counter = d_counter; a.total_out = d_total;
     a.num_tiles = num_tiles;
     a.flags = flags;
+    a.null_mode = 0;
+#ifdef UKM_MEASURE  // measurement build only (make EXTRA=-DUKM_MEASURE): the null mode produces no valid result
     {
         const char* e = getenv("UKM_SETOP_NULL");
         a.null_mode = (e && e[0] == '1') ? 1 : 0;
     }
+#endif
     a.threshold = threshold;
     a.tax = ukm_taxdev(ctx);
     a.err = ctx->d_err;
