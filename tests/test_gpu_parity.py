@@ -216,8 +216,11 @@ def test_setop_kernel_variants(eng, kernel, skew, monkeypatch):
     same(eng.union(d)[0].cpu().numpy().view(U64), exp, "unaligned union")
 
 
-def test_search_path_skewed_pairs(eng, tax):
-    """|B| >> |A|: the look-up kernel (inter/diff after a few files), keys-only and with taxids."""
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_search_path_skewed_pairs(eng, tax, mode, monkeypatch):
+    """|B| >> |A|: the look-up kernel (inter/diff after a few files), keys-only and with taxids, for every
+    look-up mode (bisection, interpolated start + gallop, anchored)."""
+    monkeypatch.setenv("UKM_SEARCH_MODE", mode)
     otax, n_tax = tax
     r = rng(77)
     big = np.unique(r.integers(0, 2**62, 3_000_000, dtype=U64))
@@ -239,6 +242,31 @@ def test_search_path_skewed_pairs(eng, tax):
         gk, gt = eng.diff(tf, has_taxid=True, compare_taxid=True)
         same(gk, ek, "search diff -t keys")
         same(gt, et, "search diff -t taxids")
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_search_path_key_distributions(eng, mode, monkeypatch):
+    """The interpolated look-up must not depend on uniform keys: clustered, stepped and extreme-valued subjects,
+    queries below / above / between all of them, windows that span everything or nothing."""
+    monkeypatch.setenv("UKM_SEARCH_MODE", mode)
+    r = rng(78)
+    dense = np.arange(5_000_000, 7_000_000, dtype=U64)                       # one long run of consecutive keys
+    clustered = np.unique(np.concatenate([r.integers(c, c + 4000, 60_000, dtype=U64)
+                                          for c in r.integers(0, 2**62, 40, dtype=U64)]))
+    stepped = np.unique(np.concatenate([np.arange(0, 300_000, dtype=U64), (U64(1) << U64(61)) + np.arange(0, 300_000, dtype=U64) * U64(977),
+                                        np.array([2**64 - 1, 2**64 - 2, 2**63], dtype=U64)]))
+    expo = np.unique((U64(1) << r.integers(0, 62, 400_000).astype(U64)) + r.integers(0, 2**20, 400_000, dtype=U64))
+    for big in (dense, clustered, stepped, expo):
+        picks = [big[r.integers(0, len(big), 3000)], big[:50], big[-50:],
+                 r.integers(0, 2**62, 2000, dtype=U64), big[r.integers(0, len(big), 3000)] + U64(1),
+                 np.array([0, 1, 2**64 - 1, 2**63], dtype=U64)]
+        small = np.unique(np.concatenate(picks))
+        for q in (small, small[:1], small[-1:], small[small < big[0]], small[small > big[-1]], small[::97].copy()):
+            if len(q) == 0 or len(q) * 6 > len(big):
+                continue
+            files = [q, big]
+            same(eng.inter(files)[0], np.intersect1d(q, big), f"inter mode {mode}")
+            same(eng.diff(files)[0], np.setdiff1d(q, big), f"diff mode {mode}")
 
 
 @pytest.mark.parametrize("N,nfiles", [(1000, 2), (20_000, 3), (300_000, 8), (2_000_000, 2), (1_500_000, 5)])

@@ -726,8 +726,8 @@ __global__ void search_partition_kernel(const uint64_t* __restrict__ A, long lon
     bpart[t] = lo;
 }
 
-template <int OP, bool TAX>
-__global__ void __launch_bounds__(SS_THREADS) setop_search_kernel(const SetopArgs p) {
+template <int OP, bool TAX, int MODE>
+__global__ void __launch_bounds__(SS_THREADS, TAX ? 6 : 8) setop_search_kernel(const SetopArgs p) {
     constexpr int NW = SS_THREADS / 32;
     __shared__ uint64_t s_o[SS_TILE];
     __shared__ uint32_t s_ot[TAX ? SS_TILE : 1];
@@ -744,22 +744,87 @@ __global__ void __launch_bounds__(SS_THREADS) setop_search_kernel(const SetopArg
         a[j] = (base + j < p.nA) ? p.A[base + j] : ~0ull;
         pos[j] = blo;
     }
-    // branch-free lower_bound (uniform trip count: n depends only on the window size), SS_ITEMS
-    // independent chains per thread.  Invariant: the answer lies in [pos, pos + n].
     long long n = bhi - blo;
-    while (n > 1) {
-        const long long half = n >> 1;
+    if (MODE != 0 && n > 64 && n < (1ll << 30)) {
+        // interpolated start + gallop + bisection: the probes of one look-up stay within a few sectors of
+        // the answer instead of spreading over the whole window (bisection reads ~12 sectors per look-up,
+        // i.e. all of B once |A| >= |B| / 64).  Mode 2 anchors items 1.. on item 0's position.
+        // Positions are 32-bit offsets into the window (larger windows take the bisection below).
+        const uint64_t* __restrict__ W = p.B + blo;
+        const int wn = (int)n;
+        const uint64_t bl = __ldg(W), bh = __ldg(W + wn - 1);
+        const float dens = (float)(wn - 1) / (float)(bh - bl + 1);
+        auto guess = [&](uint64_t x) -> int {
+            if (x <= bl) return 0;
+            if (x > bh) return wn;
+            return (int)fminf((float)(x - bl) * dens, (float)wn);
+        };
+        // One probe per item and round, the items of a thread in lock step (independent loads in flight).
+        // Every round picks q in [lo, hi) and W[q] rules one side out.  st > 0: galloping right from the
+        // guess (steps 4, 8, ..), st < 0: galloping left, st == 0: bisecting the bracket the gallop closed.
+        int lo[SS_ITEMS], hi[SS_ITEMS], st[SS_ITEMS];
+        auto first = [&](int j, int lo0, int g) {  // probe the guess: it decides the gallop's direction
+            lo[j] = lo0; hi[j] = wn; st[j] = 0;
+            if (lo0 < wn) {
+                const int q = max(lo0, min(g, wn - 1));
+                const bool lt = __ldg(W + q) < a[j];
+                if (lt) lo[j] = q + 1;
+                else hi[j] = q;
+                st[j] = lt ? 4 : -4;
+            }
+        };
+        auto rounds = [&](int j0) {
+            for (;;) {
+                bool busy = false;
 #pragma unroll
-        for (int j = 0; j < SS_ITEMS; ++j) {
-            const uint64_t v = __ldg(p.B + pos[j] + half);
-            if (v < a[j]) pos[j] += half;
+                for (int j = j0; j < SS_ITEMS; ++j) {
+                    if (lo[j] < hi[j]) {
+                        int q = st[j] > 0 ? lo[j] + st[j] - 1 : (st[j] < 0 ? hi[j] + st[j] : lo[j] + ((hi[j] - lo[j]) >> 1));
+                        q = max(lo[j], min(q, hi[j] - 1));
+                        const bool lt = __ldg(W + q) < a[j];
+                        if (lt) lo[j] = q + 1;
+                        else hi[j] = q;
+                        st[j] = ((st[j] > 0 && !lt) || (st[j] < 0 && lt)) ? 0 : st[j] * 2;  // |st| < 2 * wn < 2^31
+                        busy = true;
+                    }
+                }
+                if (!busy) break;
+            }
+        };
+        if (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < SS_ITEMS; ++j) first(j, 0, guess(a[j]));
+            rounds(0);
+        } else {
+            first(0, 0, guess(a[0]));
+#pragma unroll
+            for (int j = 1; j < SS_ITEMS; ++j) { lo[j] = 0; hi[j] = 0; st[j] = 0; }
+            rounds(0);
+            // a[j] > a[0]: the answer is at or after item 0's; the ~0 padding past nA lands on the end
+#pragma unroll
+            for (int j = 1; j < SS_ITEMS; ++j)
+                first(j, lo[0], a[j] > bh ? wn : lo[0] + (int)fminf((float)(a[j] - a[0]) * dens, (float)wn));
+            rounds(1);
         }
-        n -= half;
-    }
-    if (n == 1) {
 #pragma unroll
-        for (int j = 0; j < SS_ITEMS; ++j)
-            if (__ldg(p.B + pos[j]) < a[j]) pos[j] += 1;
+        for (int j = 0; j < SS_ITEMS; ++j) pos[j] = blo + lo[j];
+    } else {
+        // branch-free lower_bound (uniform trip count: n depends only on the window size), SS_ITEMS
+        // independent chains per thread.  Invariant: the answer lies in [pos, pos + n].
+        while (n > 1) {
+            const long long half = n >> 1;
+#pragma unroll
+            for (int j = 0; j < SS_ITEMS; ++j) {
+                const uint64_t v = __ldg(p.B + pos[j] + half);
+                if (v < a[j]) pos[j] += half;
+            }
+            n -= half;
+        }
+        if (n == 1) {
+#pragma unroll
+            for (int j = 0; j < SS_ITEMS; ++j)
+                if (__ldg(p.B + pos[j]) < a[j]) pos[j] += 1;
+        }
     }
     unsigned mask = 0;
     uint32_t tx[TAX ? SS_ITEMS : 1] = {0};
@@ -933,6 +998,30 @@ long long search_skew() {
     return e ? atoll(e) : 6;  // C3 on B200: 12.95 ms per inter at 6, 13.2 ms at 3 and at 10..16, 15.7 ms without the look-up path
 }
 
+// How the look-up kernel finds its positions (UKM_SEARCH_MODE overrides; see setop_search_kernel): 0 bisection of
+// the tile's window, 1 interpolated guess + gallop per item, 2 the same with items 1.. anchored on item 0.
+// C3 on B200 (tools/exp_search.py): inter 12.89 / 14.54 / 12.67 ms, diff 13.32 / 15.01 / 13.15 ms for 0 / 1 / 2.
+int search_mode() {
+    const char* e = getenv("UKM_SEARCH_MODE");
+    const int v = e ? atoi(e) : 2;
+    return (v >= 0 && v <= 2) ? v : 2;
+}
+
+template <int OP>
+void launch_search(ukm_ctx* ctx, bool tax, int mode, const SetopArgs& a) {
+#define UKM_SS(T, M) setop_search_kernel<OP, T, M><<<a.num_tiles, SS_THREADS, 0, ctx->stream>>>(a)
+    if (tax) {
+        if (mode == 1) UKM_SS(true, 1);
+        else if (mode == 2) UKM_SS(true, 2);
+        else UKM_SS(true, 0);
+    } else {
+        if (mode == 1) UKM_SS(false, 1);
+        else if (mode == 2) UKM_SS(false, 2);
+        else UKM_SS(false, 0);
+    }
+#undef UKM_SS
+}
+
 // out buffers must hold: INTER min(nA,nB); DIFF nA; UNION/MERGE nA+nB.  *n_out gets the count
 // (host value, after a stream sync).
 int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, bool cnt, unsigned flags, uint32_t threshold,
@@ -988,13 +1077,8 @@ int setop2(ukm_ctx* ctx, int op, const DevSet& A, const DevSet& B, bool tax, boo
         if (use_search) {
             search_partition_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(A.k, nA, B.k, nB, num_tiles, d_part);
             UKM_LAUNCHED(ctx);
-            if (op == OP_INTER) {
-                if (tax) setop_search_kernel<OP_INTER, true><<<num_tiles, SS_THREADS, 0, ctx->stream>>>(a);
-                else setop_search_kernel<OP_INTER, false><<<num_tiles, SS_THREADS, 0, ctx->stream>>>(a);
-            } else {
-                if (tax) setop_search_kernel<OP_DIFF, true><<<num_tiles, SS_THREADS, 0, ctx->stream>>>(a);
-                else setop_search_kernel<OP_DIFF, false><<<num_tiles, SS_THREADS, 0, ctx->stream>>>(a);
-            }
+            if (op == OP_INTER) launch_search<OP_INTER>(ctx, tax, search_mode(), a);
+            else launch_search<OP_DIFF>(ctx, tax, search_mode(), a);
             UKM_LAUNCHED(ctx);
             r = UKM_OK;
         } else {
