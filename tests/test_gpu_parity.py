@@ -218,7 +218,7 @@ def test_setop_kernel_variants(eng, kernel, skew, monkeypatch):
 
 @pytest.mark.parametrize("mode", ["0", "1", "2"])
 def test_search_path_skewed_pairs(eng, tax, mode, monkeypatch):
-    """|B| >> |A|: the look-up kernel (inter/diff after a few files), keys-only and with taxids, for every
+    """|B| >> |A|: the look-up kernels (inter/diff after a few files), keys-only and with taxids, for every
     look-up mode (bisection, interpolated start + gallop, anchored)."""
     monkeypatch.setenv("UKM_SEARCH_MODE", mode)
     otax, n_tax = tax
