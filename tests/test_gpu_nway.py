@@ -200,3 +200,100 @@ def test_nway_filter_misaligned_device_pointers(eng, monkeypatch):
     h = [x.cpu().numpy().view(U64) for x in d]
     same(eng.inter(d)[0].cpu().numpy().view(U64), exp_inter(h), "misaligned inter")
     same(eng.diff(d)[0].cpu().numpy().view(U64), exp_diff(h), "misaligned diff")
+
+
+# ---------------------------------------------------------------------------------------
+# single-pass inter / diff over file-0 chunks (unikmer_b200/csrc/nfilter.cu, the default keys-only path)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", ["0", "1"])
+@pytest.mark.parametrize("sub", ["0", "64", "32", "16", "8"])
+@pytest.mark.parametrize("nf", [2, 3, 5, 8])
+def test_nfilter_shapes(eng, cfg, sub, nf, monkeypatch):
+    """Every tile shape (file-0 keys per warp x slot size); a forced shape that is too large for the size ratio
+    sends segments down the global-memory look-up path of a tile."""
+    monkeypatch.setenv("UKM_NFILTER_CFG", cfg)
+    monkeypatch.setenv("UKM_NFILTER_SUB", sub)
+    monkeypatch.setenv("UKM_NFILTER_FORCE", "1")
+    for N in (3_000, 250_000, 2_500_000):
+        files = member_files(N, nf)
+        same(eng.inter(files)[0], oracle.inter(files)[0], f"inter cfg {cfg} sub {sub} nf {nf} N {N}")
+        same(eng.diff(files)[0], oracle.diff(files)[0], f"diff cfg {cfg} sub {sub} nf {nf} N {N}")
+
+
+def test_nfilter_is_the_default_path(eng):
+    files = member_files(600_000, 8)
+    eng.stats_reset()
+    eng.stats_enable(True)
+    gi, gd = eng.inter(files)[0], eng.diff(files)[0]
+    eng.stats_enable(False)
+    st = eng.stats()
+    assert st.get("setop_inter_nway", {}).get("launches") == 1 and st.get("setop_diff_nway", {}).get("launches") == 1, st
+    same(gi, oracle.inter(files)[0], "inter default")
+    same(gd, oracle.diff(files)[0], "diff default")
+
+
+@pytest.mark.parametrize("nf", [9, 15, 16, 20])
+def test_nfilter_more_than_eight_files(eng, nf, monkeypatch):
+    monkeypatch.setenv("UKM_NFILTER_FORCE", "1")
+    r = rng(nf)
+    uni = np.unique(r.integers(0, 2**62, 300_000, dtype=U64))
+    files = [uni[r.random(len(uni)) < 0.9] for _ in range(nf)]
+    same(eng.inter(files)[0], exp_inter(files), f"inter of {nf} files")
+    files = [uni[r.random(len(uni)) < 0.5]] + [uni[r.random(len(uni)) < 0.1] for _ in range(nf - 1)]
+    same(eng.diff(files)[0], exp_diff(files), f"diff of {nf} files")
+
+
+@pytest.mark.parametrize("sub", ["0", "64", "8"])
+def test_nfilter_distributions(eng, sub, monkeypatch):
+    monkeypatch.setenv("UKM_NFILTER_FORCE", "1")
+    monkeypatch.setenv("UKM_NFILTER_SUB", sub)
+    r = rng(21)
+    cases = {}
+    base = np.unique(r.integers(0, 2**64, 300_000, dtype=U64))
+    fs = [base[r.random(len(base)) < 0.7] for _ in range(8)]
+    for q in (0, 3, 7):
+        fs[q] = np.unique(np.concatenate([fs[q], np.array([0, 2**64 - 1], dtype=U64)]))
+    cases["extremes"] = fs
+    cases["identical"] = [base.copy() for _ in range(5)]
+    big0 = np.unique(np.concatenate([r.integers(0, 2**63, 20_000, dtype=U64), U64(10**12) + np.arange(300_000, dtype=U64)]))
+    cases["file0_dense"] = [big0] + [np.unique(np.concatenate([r.integers(0, 2**63, 20_000, dtype=U64),
+                                                               U64(10**12) + np.arange(0, 300_000, 3 + q, dtype=U64)])) for q in range(4)]
+    # subjects locally far denser than file 0 (runs of consecutive integers where file 0 has a handful of keys):
+    # those segments do not fit a slot and are probed in global memory
+    sparse0 = np.unique(np.concatenate([r.integers(0, 2**63, 30_000, dtype=U64), U64(10**12) + np.arange(0, 400_000, 997, dtype=U64)]))
+    cases["subjects_dense"] = [sparse0] + [np.unique(np.concatenate([r.integers(0, 2**63, 30_000, dtype=U64),
+                                                                     U64(10**12) + np.arange(q, 400_000, 1 + q, dtype=U64)])) for q in range(5)]
+    cases["tiny_extremes"] = [np.array([0, 5, 9, 2**64 - 1], dtype=U64), np.array([0, 9, 2**64 - 1], dtype=U64),
+                              np.array([5, 9, 2**64 - 1], dtype=U64)]
+    cases["one_key"] = [np.array([7], dtype=U64), np.array([7], dtype=U64), np.array([1, 7, 9], dtype=U64)]
+    cases["disjoint"] = [np.unique(r.integers(q << 50, (q << 50) + 2**30, 5000 << (q % 5), dtype=U64)) for q in range(6)]
+    cases["geometric"] = [np.unique(np.exp2(r.random(150_000) * 40 + 20).astype(U64)) for _ in range(8)]
+    cases["small_first"] = [base[::50].copy()] + [base[r.random(len(base)) < 0.8] for _ in range(4)]
+    cases["big_first"] = [base.copy()] + [base[::40 + q].copy() for q in range(4)]
+    cases["subject_below_and_above"] = [base[1000:2000].copy(), base.copy(), base[::2].copy()]
+    cases["with_empty_subject"] = [base[::2].copy(), base[::3].copy(), np.zeros(0, dtype=U64), base[::5].copy(), base[::7].copy()]
+    for name, files in cases.items():
+        same(eng.inter(files)[0], oracle.inter(files)[0], f"inter {name} sub {sub}")
+        exp = exp_diff(files) if name == "with_empty_subject" else oracle.diff(files)[0]
+        same(eng.diff(files)[0], exp, f"diff {name} sub {sub}")
+
+
+def test_nfilter_tile_and_mask_block_seams(eng, monkeypatch):
+    """File-0 lengths around multiples of the warp group (64), the tile (512) and the gather block (2048 masks)."""
+    monkeypatch.setenv("UKM_NFILTER_FORCE", "1")
+    r = rng(5)
+    base = np.unique(r.integers(0, 2**62, 600_000, dtype=U64))
+    for n0 in (1, 63, 64, 65, 511, 512, 513, 4095, 4096, 4097, 64 * 2048 - 1, 64 * 2048, 64 * 2048 + 1, 300_001):
+        files = [base[:n0].copy()] + [base[r.random(len(base)) < 0.6] for _ in range(3)]
+        same(eng.inter(files)[0], exp_inter(files), f"inter n0 {n0}")
+        same(eng.diff(files)[0], exp_diff(files), f"diff n0 {n0}")
+
+
+def test_nfilter_misaligned_device_pointers(eng, monkeypatch):
+    import torch
+    monkeypatch.setenv("UKM_NFILTER_FORCE", "1")
+    files = member_files(700_000, 6)
+    d = [torch.from_numpy(f.view(np.int64)).cuda()[(i % 2):] for i, f in enumerate(files)]
+    h = [x.cpu().numpy().view(U64) for x in d]
+    same(eng.inter(d)[0].cpu().numpy().view(U64), exp_inter(h), "misaligned inter")
+    same(eng.diff(d)[0].cpu().numpy().view(U64), exp_diff(h), "misaligned diff")

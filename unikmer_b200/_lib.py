@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libukm.so")
+# UKM_LIB_VARIANT=measure (tools/exp_*.py only): the -DUKM_MEASURE build with the pipelines' null modes
+LIB_PATH = os.path.join(_HERE, "libukm_measure.so" if os.environ.get("UKM_LIB_VARIANT") == "measure" else "libukm.so")
 
 OK, E_ARG, E_CUDA, E_NOMEM, E_CAPACITY, E_NOT_SORTED_UNIQUE, E_ILLEGAL_BASE, E_NO_TAXONOMY, E_PANIC, E_INTERNAL = (
     0, -1, -2, -3, -4, -5, -6, -7, -8, -9)

@@ -146,6 +146,11 @@ int ukm_nway_union(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, i
 int ukm_nway_filter(ukm_ctx* ctx, bool inter, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
                     bool* fell_back);
 
+// single-pass N-way inter / diff over file-0 chunks (nfilter.cu): keys[0] filtered by membership in keys[1..nf-1]
+bool ukm_nfilter_enabled();
+int ukm_nfilter(ukm_ctx* ctx, bool inter, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
+                bool* declined);
+
 static inline int ukm_grid_for(size_t work, int per_block, int sm_count, int max_per_sm = 32) {
     size_t g = (work + per_block - 1) / per_block;
     size_t cap = (size_t)sm_count * max_per_sm;

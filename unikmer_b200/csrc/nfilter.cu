@@ -1,0 +1,624 @@
+// nfilter.cu -- single-pass N-way inter / diff of sorted duplicate-free k-mer streams (keys only).
+//
+// Replaces the file-by-file iteration of inter.go:205-286 (mc <- mc AND file_i, compact after every file) and
+// diff.go:380-435 (two-pointer walk + map rebuild per subject) for up to eight files per pass with ONE read of every
+// input: the result is file 0 filtered by membership in files 1..nf-1 (inter: found in all, diff: found in none), which
+// is exactly what the reference's iteration produces on duplicate-free inputs.
+//
+// Tiles are chunks of FILE 0 (M = 8 * SUB consecutive keys); the matching segment of every other file is
+// [lower_bound(F_f, first key of the chunk), lower_bound(F_f, first key of the next chunk)) -- one direct search per
+// file and boundary (nfilter_partition_kernel), no multi-sequence selection.  A persistent CTA streams its tiles
+// (round-robin) through a ring of shared-memory slots: the loader warp brings the eight segments in with 1-D TMA bulk
+// copies several tiles ahead; each of the eight consumer warps owns SUB file-0 keys of the tile, narrows every other
+// segment to its own key range, and runs the reference's per-file early exit on its keys -- survivors are
+// re-compacted inside the warp after every file, the last files are probed as (survivor, file) pairs.  The warp's
+// result is ONE 64-bit survivor mask per SUB keys, written to global memory: no output offsets, no look-back, no
+// block-wide barrier, no dependency between CTAs (the kernel is correct under any scheduling).  A second, small pass
+// (count / scan / gather) turns the masks into the compact sorted result.
+//
+// A segment that does not fit the slot (file f is locally much denser than file 0) is not loaded: the warps look their
+// keys up in global memory for that file and that tile.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "nway_core.cuh"
+
+namespace {
+
+constexpr int NF_WARPS = 8;                       // consumer warps per CTA
+constexpr int NF_THREADS = NF_WARPS * 32 + 32;    // + the loader warp (warp 0)
+constexpr int NF_S0 = 64;                         // partition: every NF_S0-th boundary is searched in the whole file first
+
+enum { NFOP_INTER = 0, NFOP_DIFF = 1 };
+
+// ---------------------------------------------------------------------------------------------------
+// partition: bounds[t].pos[f] = first element of file f that belongs to tile t; bounds[num_tiles] = the end
+// ---------------------------------------------------------------------------------------------------
+struct NfPartArgs {
+    NwFiles F;
+    long long n0;
+    int M;          // file-0 keys per tile
+    int num_tiles;
+};
+
+// Level 0 (parent = 0): boundaries at multiples of `stride` and the end boundary, searched in the whole files, starting
+// at the position file 0 suggests.  Level 1: every other boundary inside the bracket of its two level-0 neighbours.
+__global__ void nfilter_partition_kernel(const NfPartArgs a, NwBound* __restrict__ bounds, int stride, int parent) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long t = i * stride;
+    NwBound lo, hi, out;
+    if (parent == 0) {
+        const long long first_past = ((long long)a.num_tiles + stride - 1) / stride;  // first i with i * stride >= num_tiles
+        if (i > first_past) return;
+        if (i == first_past) t = a.num_tiles;  // this thread produces the end boundary
+#pragma unroll
+        for (int f = 0; f < NW_MAX; ++f) {
+            lo.pos[f] = 0;
+            hi.pos[f] = f < a.F.nf ? a.F.n[f] : 0;
+        }
+    } else {
+        if (t >= a.num_tiles || t % parent == 0) return;
+        const long long pl = t / parent * parent;
+        const long long ph = pl + parent < a.num_tiles ? pl + parent : a.num_tiles;
+        lo = bounds[pl];
+        hi = bounds[ph];
+    }
+    const bool end = t == a.num_tiles;
+    const long long p0 = end ? a.n0 : t * a.M;
+    const uint64_t key = a.F.k[0][end ? a.n0 - 1 : p0];
+    const double frac = parent == 0 ? (double)p0 / (double)a.n0
+                                    : (double)(p0 - lo.pos[0]) / (double)(hi.pos[0] - lo.pos[0] > 0 ? hi.pos[0] - lo.pos[0] : 1);
+    lo.pos[0] = hi.pos[0] = p0;  // file 0 is cut by position, not searched
+    nw_cut_at(a.F, key, lo, hi, frac, &out);
+    if (end) {
+        // everything up to and INCLUDING the last key of file 0 belongs to the last tile
+#pragma unroll
+        for (int f = 1; f < NW_MAX; ++f)
+            if (f < a.F.nf && out.pos[f] < a.F.n[f] && a.F.k[f][out.pos[f]] == key) ++out.pos[f];
+    }
+    out.pos[0] = p0;
+    bounds[t] = out;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the tile kernel
+// ---------------------------------------------------------------------------------------------------
+struct NfArgs {
+    NwFiles F;
+    const NwBound* bounds;
+    unsigned long long* masks;  // one word per SUB keys of file 0: bit j = key j of the group survives
+    int num_tiles;
+    int null_mode;  // measurement aids (UKM_MEASURE builds, results NOT valid): 1 = consumers do no work, 2 = also no loads, 3 = narrowing only
+    int* err;
+};
+
+struct NfGeom {
+    int n[NW_MAX];          // elements of file f in the slot; -1: the segment stayed in global memory
+    int off[NW_MAX];        // first element of the segment in the slot
+    long long gpos[NW_MAX]; // global segment [gpos, gpos + gn)
+    long long gn[NW_MAX];
+};
+
+struct NfSub {  // a warp's share of a segment
+    long long lo, n;
+};
+
+__device__ __forceinline__ int nf_slice_h(const uint64_t* g, long long start) {
+    return (int)((reinterpret_cast<uintptr_t>(g + start) & 15u) >> 3);
+}
+
+// lower_bound of x in seg[0, n); *eq = the element there equals x.  The element at the answer is always the last
+// probe that was not below x (or the answer is n), so equality needs no extra load.
+template <typename IDX>
+__device__ __forceinline__ IDX nf_lower_bound(const uint64_t* seg, IDX n, uint64_t x, bool* eq) {
+    IDX lo = 0, len = n;
+    bool e = false;
+    while (len > 0) {
+        const IDX half = len >> 1;
+        const uint64_t v = seg[lo + half];
+        const bool lt = v < x;
+        e = lt ? e : (v == x);
+        lo = lt ? lo + half + 1 : lo;
+        len = lt ? len - half - 1 : half;
+    }
+    *eq = e;
+    return lo;
+}
+
+// two keys against the same segment, probes interleaved (two independent load chains)
+__device__ __forceinline__ void nf_contains2(const uint64_t* seg, int n, uint64_t x0, uint64_t x1, bool* f0, bool* f1) {
+    int lo0 = 0, lo1 = 0;
+    bool e0 = false, e1 = false;
+    int len0 = n, len1 = n;
+    while (len0 > 0 || len1 > 0) {
+        const int h0 = len0 >> 1, h1 = len1 >> 1;
+        const uint64_t v0 = seg[lo0 + h0];  // reading seg[lo + 0] with len = 0 stays inside the slot (padding)
+        const uint64_t v1 = seg[lo1 + h1];
+        const bool lt0 = v0 < x0, lt1 = v1 < x1;
+        if (len0 > 0) {
+            e0 = lt0 ? e0 : (v0 == x0);
+            lo0 = lt0 ? lo0 + h0 + 1 : lo0;
+            len0 = lt0 ? len0 - h0 - 1 : h0;
+        }
+        if (len1 > 0) {
+            e1 = lt1 ? e1 : (v1 == x1);
+            lo1 = lt1 ? lo1 + h1 + 1 : lo1;
+            len1 = lt1 ? len1 - h1 - 1 : h1;
+        }
+    }
+    *f0 = e0;
+    *f1 = e1;
+}
+
+template <int SUB, int CAP>
+struct NfShape {
+    static constexpr int M = NF_WARPS * SUB;
+    static constexpr int SLOT_E = (CAP + 2 * NW_MAX + 2 + 1) & ~1;  // + per-segment alignment slack + read-past padding
+};
+
+template <int OP, int SUB, int CAP, int SLOTS>
+__global__ void __launch_bounds__(NF_THREADS, 2) nfilter_kernel(const NfArgs p) {
+    using SH = NfShape<SUB, CAP>;
+    extern __shared__ __align__(16) unsigned char nf_smem[];
+    uint64_t* s_slots = reinterpret_cast<uint64_t*>(nf_smem);  // SLOTS * SLOT_E
+    __shared__ __align__(8) uint64_t full_bar[SLOTS], empty_bar[SLOTS];
+    __shared__ NfGeom s_geom[SLOTS];
+    __shared__ const uint64_t* s_fk[NW_MAX];
+    __shared__ NfSub s_sub[NF_WARPS][NW_MAX];
+    __shared__ uint8_t s_list[NF_WARPS][64];
+
+    const int G = gridDim.x;
+    const int n_my = (p.num_tiles - (int)blockIdx.x + G - 1) / G;
+    const int nf = p.F.nf;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SLOTS; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NF_WARPS);
+        }
+#pragma unroll
+        for (int f = 0; f < NW_MAX; ++f) s_fk[f] = p.F.k[f];
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const unsigned lane = lane_id();
+
+    if (threadIdx.x < 32) {
+        // ================= loader warp: lane f owns file f =================
+        const bool mine = (int)lane < nf;
+        const uint64_t* fk = mine ? s_fk[lane] : nullptr;
+        // software pipeline: cut positions two tiles ahead, the unaligned head / tail elements one tile ahead, so
+        // that no global-memory latency sits between two tiles of the loader
+        long long lo_a = 0, nn_a = 0, lo_b = 0, nn_b = 0;
+        uint64_t hv_a = 0, tv_a = 0;
+        auto fetch_bounds = [&](int li, long long* lo, long long* nn) {
+            *lo = 0;
+            *nn = 0;
+            if (mine && li < n_my) {
+                const int t = (int)blockIdx.x + li * G;
+                *lo = p.bounds[t].pos[lane];
+                *nn = p.bounds[t + 1].pos[lane] - *lo;
+            }
+        };
+        auto fetch_edges = [&](long long lo, long long nn, uint64_t* hv, uint64_t* tv) {
+            *hv = 0;
+            *tv = 0;
+            if (mine && nn > 0 && nn <= CAP) {
+                *hv = fk[lo];
+                *tv = fk[lo + nn - 1];
+            }
+        };
+        fetch_bounds(0, &lo_a, &nn_a);
+        fetch_edges(lo_a, nn_a, &hv_a, &tv_a);
+        fetch_bounds(1, &lo_b, &nn_b);
+        for (int li = 0; li < n_my; ++li) {
+            const int s = li % SLOTS, u = li / SLOTS;
+            uint64_t hv_b, tv_b;
+            long long lo_c, nn_c;
+            fetch_edges(lo_b, nn_b, &hv_b, &tv_b);  // in flight until the next iteration uses them
+            fetch_bounds(li + 2, &lo_c, &nn_c);
+            if (u > 0 && !mbar_wait(&empty_bar[s], (unsigned)(u - 1) & 1u)) {
+                if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+            }
+            const long long lo = lo_a, nn = nn_a;
+            if (__any_sync(0xffffffffu, nn < 0)) {  // cannot happen: the cuts of a sorted file are monotone
+                if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+            }
+            // greedy layout in file order: a segment goes into the slot if it still fits, else it stays in global memory
+            const int h = (mine && nn > 0) ? nf_slice_h(fk, lo) : 0;
+            const int padded = (mine && nn > 0 && nn <= CAP) ? (int)((h + nn + 1) & ~1ll) : 0;
+            int base = 0, my_base = 0;
+            bool my_fit = false;
+#pragma unroll
+            for (int f = 0; f < NW_MAX; ++f) {
+                const int pf = __shfl_sync(0xffffffffu, padded, f);
+                const long long nnf = __shfl_sync(0xffffffffu, nn, f);
+                const bool fit = nnf <= 0 || (nnf <= CAP && base + pf <= CAP);
+                if ((int)lane == f) {
+                    my_fit = fit;
+                    my_base = base;
+                }
+                if (fit) base += pf;
+            }
+            uint64_t* slot = s_slots + (size_t)s * SH::SLOT_E;
+            const int n = my_fit ? (int)(nn > 0 ? nn : 0) : 0;
+            int head = 0, body = 0;
+            if (n > 0) {
+                head = h ? 1 : 0;
+                body = (n - head) & ~1;
+                if (head) slot[my_base + h] = hv_a;
+                if (head + body < n) slot[my_base + h + n - 1] = tv_a;
+            }
+            if (p.null_mode == 2) {  // measurement aid: the barrier ring alone
+                if (mine) s_geom[s].n[lane] = 0;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[s]);
+            } else {
+            unsigned bytes = (unsigned)body * 8u;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
+            if (mine) {
+                s_geom[s].n[lane] = my_fit ? n : -1;
+                s_geom[s].off[lane] = my_base + h;
+                s_geom[s].gpos[lane] = lo;
+                s_geom[s].gn[lane] = nn;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&full_bar[s], bytes);  // arrive (release: plain stores + geometry) + tx count
+            __syncwarp();
+            if (body) tma_load_1d(slot + my_base + h + head, fk + lo + head, (unsigned)body * 8u, &full_bar[s]);
+            }
+            lo_a = lo_b; nn_a = nn_b; hv_a = hv_b; tv_a = tv_b;
+            lo_b = lo_c; nn_b = nn_c;
+        }
+        return;
+    }
+
+    // ================= consumer warps: SUB keys of file 0 each, no block-wide synchronisation =================
+    const int w = ((int)threadIdx.x >> 5) - 1;
+    uint8_t* list = s_list[w];
+    NfSub* sub = s_sub[w];
+    for (int i = 0; i < n_my; ++i) {
+        const int s = i % SLOTS, u = i / SLOTS;
+        const int tile = (int)blockIdx.x + i * G;
+        const uint64_t* slot = s_slots + (size_t)s * SH::SLOT_E;
+        if (!mbar_wait(&full_bar[s], (unsigned)u & 1u)) {
+            if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
+        }
+        const NfGeom& g = s_geom[s];
+        const int n0t = g.n[0];
+        int cnt = n0t - w * SUB;
+        cnt = cnt < 0 ? 0 : (cnt > SUB ? SUB : cnt);
+        unsigned long long alive = cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull);
+        const uint64_t* f0 = slot + g.off[0] + w * SUB;
+        if (cnt > 0 && p.null_mode != 1 && p.null_mode != 2) {
+            // ---- narrow every segment to this warp's key range: lanes 0..7 the lower end, lanes 8..15 the upper end ----
+            {
+                const int f = (int)lane & 7;
+                const bool upper = lane >= 8;
+                long long pos = 0;
+                if (lane < 16 && f >= 1 && f < nf) {
+                    const bool to_end = upper && (w * SUB + cnt >= n0t);  // the last warp of the tile takes the rest
+                    const uint64_t key = upper ? (to_end ? 0 : f0[cnt]) : f0[0];
+                    bool eq;
+                    if (g.n[f] >= 0) {
+                        pos = to_end ? g.n[f] : nf_lower_bound<int>(slot + g.off[f], g.n[f], key, &eq);
+                    } else {
+                        pos = to_end ? g.gn[f] : nf_lower_bound<long long>(s_fk[f] + g.gpos[f], g.gn[f], key, &eq);
+                    }
+                }
+                const long long hi = __shfl_down_sync(0xffffffffu, pos, 8);
+                if (lane < 8 && f >= 1 && f < nf) {
+                    sub[f].lo = pos;
+                    sub[f].n = hi - pos;
+                }
+            }
+            __syncwarp();
+            // ---- file by file with early exit; survivors are re-listed after every file ----
+            int f = p.null_mode == 3 ? nf : 1;
+            while (f < nf && alive) {
+                const int a = __popcll(alive);
+                const int R = nf - f;
+                if (alive >> lane & 1ull) list[__popcll(alive & ((1ull << lane) - 1ull))] = (uint8_t)lane;
+                if (SUB > 32 && (alive >> (lane + 32) & 1ull)) list[__popcll(alive & ((1ull << (lane + 32)) - 1ull))] = (uint8_t)(lane + 32);
+                __syncwarp();
+                unsigned long long kill = 0;
+                if (a * R > 64 || R == 1) {
+                    // one file, every survivor
+                    const long long slo = sub[f].lo, sn = sub[f].n;
+                    if (g.n[f] >= 0) {
+                        const uint64_t* seg = slot + g.off[f] + (int)slo;
+                        const int i0 = lane < (unsigned)a ? list[lane] : 0;
+                        if (a > 32) {
+                            const bool v1 = (int)lane + 32 < a;
+                            const int i1 = v1 ? list[lane + 32] : i0;
+                            bool fd0, fd1;
+                            nf_contains2(seg, (int)sn, f0[i0], f0[i1], &fd0, &fd1);
+                            if (OP == NFOP_INTER ? !fd0 : fd0) kill |= 1ull << i0;
+                            if (v1 && (OP == NFOP_INTER ? !fd1 : fd1)) kill |= 1ull << i1;
+                        } else if ((int)lane < a) {
+                            bool fd;
+                            nf_lower_bound<int>(seg, (int)sn, f0[i0], &fd);
+                            if (OP == NFOP_INTER ? !fd : fd) kill |= 1ull << i0;
+                        }
+                    } else {
+                        const uint64_t* seg = s_fk[f] + g.gpos[f] + slo;
+                        for (int j = (int)lane; j < a; j += 32) {
+                            const int ix = list[j];
+                            bool fd;
+                            nf_lower_bound<long long>(seg, sn, f0[ix], &fd);
+                            if (OP == NFOP_INTER ? !fd : fd) kill |= 1ull << ix;
+                        }
+                    }
+                    f += 1;
+                } else {
+                    // the remaining files together: one (survivor, file) pair per lane and round
+                    const int pairs = a * R;
+                    for (int q = (int)lane; q < pairs; q += 32) {
+                        const int si = q / R, ff = f + (q - si * R);
+                        const int ix = list[si];
+                        const long long slo = sub[ff].lo, sn = sub[ff].n;
+                        bool fd;
+                        if (g.n[ff] >= 0) nf_lower_bound<int>(slot + g.off[ff] + (int)slo, (int)sn, f0[ix], &fd);
+                        else nf_lower_bound<long long>(s_fk[ff] + g.gpos[ff] + slo, sn, f0[ix], &fd);
+                        if (OP == NFOP_INTER ? !fd : fd) kill |= 1ull << ix;
+                    }
+                    f = nf;
+                }
+                const unsigned klo = __reduce_or_sync(0xffffffffu, (unsigned)kill);
+                const unsigned khi = SUB > 32 ? __reduce_or_sync(0xffffffffu, (unsigned)(kill >> 32)) : 0u;
+                alive &= ~(((unsigned long long)khi << 32) | klo);
+                __syncwarp();  // the list is rewritten in the next round
+            }
+        }
+        if (lane == 0) p.masks[(size_t)tile * NF_WARPS + w] = alive;
+        __syncwarp();  // every lane is past its reads of the slot
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// masks -> compact sorted result: per-block survivor counts, one scan, gather
+// ---------------------------------------------------------------------------------------------------
+constexpr int NG_THREADS = 256;
+constexpr int NG_PER = 8;                            // mask words per thread
+constexpr int NG_BLOCK = NG_THREADS * NG_PER;        // mask words per block
+
+__global__ void __launch_bounds__(NG_THREADS) nfilter_count_kernel(const unsigned long long* __restrict__ masks, size_t n_masks,
+                                                                   unsigned long long* __restrict__ block_sums) {
+    __shared__ unsigned s_w[NG_THREADS / 32];
+    const size_t base = (size_t)blockIdx.x * NG_BLOCK;
+    unsigned c = 0;
+#pragma unroll
+    for (int q = 0; q < NG_PER; ++q) {
+        const size_t i = base + (size_t)q * NG_THREADS + threadIdx.x;
+        if (i < n_masks) c += (unsigned)__popcll(masks[i]);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int q = 0; q < NG_THREADS / 32; ++q) t += s_w[q];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of nb block sums in place (one CTA), total -> *total
+__global__ void __launch_bounds__(1024) nfilter_scan_kernel(unsigned long long* __restrict__ sums, int nb, unsigned long long* __restrict__ total) {
+    __shared__ unsigned long long s_w[33];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + (int)threadIdx.x;
+        const unsigned long long v = i < nb ? sums[i] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((threadIdx.x & 31) >= (unsigned)d) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned long long x = s_w[threadIdx.x];
+            unsigned long long xi = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, xi, d);
+                if (threadIdx.x >= (unsigned)d) xi += t;
+            }
+            s_w[threadIdx.x] = xi - x;
+            if (threadIdx.x == 31) s_w[32] = xi;
+        }
+        __syncthreads();
+        if (i < nb) sums[i] = s_carry + s_w[threadIdx.x >> 5] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += s_w[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+// block b writes the survivors of its NG_BLOCK mask words; a warp owns 32 * NG_PER consecutive words
+template <int SUB>
+__global__ void __launch_bounds__(NG_THREADS) nfilter_gather_kernel(const unsigned long long* __restrict__ masks, size_t n_masks,
+                                                                    const uint64_t* __restrict__ F0, const unsigned long long* __restrict__ block_offs,
+                                                                    uint64_t* __restrict__ out) {
+    __shared__ unsigned s_w[NG_THREADS / 32 + 1];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t wbase = (size_t)blockIdx.x * NG_BLOCK + (size_t)wid * 32 * NG_PER;
+    unsigned long long m[NG_PER];
+    unsigned c = 0;
+#pragma unroll
+    for (int q = 0; q < NG_PER; ++q) {
+        const size_t i = wbase + (size_t)q * 32 + lane;
+        m[q] = i < n_masks ? masks[i] : 0ull;
+        c += (unsigned)__popcll(m[q]);
+    }
+    unsigned wtot = c;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) wtot += __shfl_xor_sync(0xffffffffu, wtot, d);
+    if (lane == 0) s_w[wid] = wtot;
+    __syncthreads();
+    unsigned long long o = block_offs[blockIdx.x];
+    for (unsigned q = 0; q < wid; ++q) o += s_w[q];
+    if (wtot == 0) return;
+#pragma unroll
+    for (int q = 0; q < NG_PER; ++q) {
+        const unsigned cq = (unsigned)__popcll(m[q]);
+        unsigned incl = cq;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned)d) incl += t;
+        }
+        const unsigned excl = incl - cq;
+        unsigned nz = __ballot_sync(0xffffffffu, cq != 0);
+        while (nz) {
+            const int src = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const unsigned long long mm = __shfl_sync(0xffffffffu, m[q], src);
+            const unsigned eo = __shfl_sync(0xffffffffu, excl, src);
+            const size_t kbase = (wbase + (size_t)q * 32 + src) * SUB;
+            if (mm >> lane & 1ull) out[o + eo + __popcll(mm & ((1ull << lane) - 1ull))] = F0[kbase + lane];
+            if (SUB > 32 && (mm >> (lane + 32) & 1ull)) out[o + eo + __popcll(mm & ((1ull << (lane + 32)) - 1ull))] = F0[kbase + lane + 32];
+        }
+        o += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+int nf_env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <int OP, int SUB, int CAP, int SLOTS>
+int launch_nfilter(ukm_ctx* ctx, NfArgs a, NfPartArgs pa, ukm_tmp& tmp, const uint64_t* F0, uint64_t* outK, size_t* n_out) {
+    using SH = NfShape<SUB, CAP>;
+    constexpr size_t smem = (size_t)SLOTS * SH::SLOT_E * 8;
+    auto kern = nfilter_kernel<OP, SUB, CAP, SLOTS>;
+    // per launch: the attribute belongs to the device of the current context (one process may own several GPUs)
+    UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NF_THREADS, smem));
+    if (per_sm < 1) return ukm_fail(ctx, UKM_E_INTERNAL, "nfilter_kernel does not fit on an SM");
+    pa.M = SH::M;
+    const int num_tiles = (int)((pa.n0 + SH::M - 1) / SH::M);
+    pa.num_tiles = num_tiles;
+    const size_t n_masks = (size_t)num_tiles * NF_WARPS;
+    const int nb = (int)((n_masks + NG_BLOCK - 1) / NG_BLOCK);
+    NwBound* d_bounds = nullptr;
+    unsigned long long* d_masks = nullptr;
+    unsigned long long* d_sums = nullptr;
+    UKM_TRY(tmp.alloc(&d_bounds, (size_t)num_tiles + 1));
+    UKM_TRY(tmp.alloc(&d_masks, n_masks));
+    UKM_TRY(tmp.alloc(&d_sums, (size_t)nb + 1));
+    {
+        const int n0 = num_tiles / NF_S0 + 2;
+        nfilter_partition_kernel<<<(n0 + 63) / 64, 64, 0, ctx->stream>>>(pa, d_bounds, NF_S0, 0);
+        UKM_LAUNCHED(ctx);
+        nfilter_partition_kernel<<<(num_tiles + 127) / 128, 128, 0, ctx->stream>>>(pa, d_bounds, 1, NF_S0);
+        UKM_LAUNCHED(ctx);
+    }
+    a.bounds = d_bounds;
+    a.masks = d_masks;
+    a.num_tiles = num_tiles;
+    int grid = per_sm * ctx->sm_count;
+    if (grid > num_tiles) grid = num_tiles;
+    kern<<<grid, NF_THREADS, smem, ctx->stream>>>(a);
+    UKM_LAUNCHED(ctx);
+    nfilter_count_kernel<<<nb, NG_THREADS, 0, ctx->stream>>>(d_masks, n_masks, d_sums);
+    UKM_LAUNCHED(ctx);
+    nfilter_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_sums, nb, d_sums + nb);
+    UKM_LAUNCHED(ctx);
+    nfilter_gather_kernel<SUB><<<nb, NG_THREADS, 0, ctx->stream>>>(d_masks, n_masks, F0, d_sums, outK);
+    UKM_LAUNCHED(ctx);
+    UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_sums + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = (size_t)ctx->h_scratch[0];
+    tmp.free_now(d_bounds);
+    tmp.free_now(d_masks);
+    tmp.free_now(d_sums);
+    return UKM_OK;
+}
+
+template <int OP>
+int launch_nfilter_sub(ukm_ctx* ctx, int sub, const NfArgs& a, const NfPartArgs& pa, ukm_tmp& tmp, const uint64_t* F0, uint64_t* outK,
+                       size_t* n_out) {
+    // slot capacity x ring depth: 3 x 36 KB (two CTAs per SM); UKM_NFILTER_CFG=1: 4 x 27 KB for A/B runs
+    const int cfg = nf_env_int("UKM_NFILTER_CFG", 0);
+    if (cfg == 1) {
+        switch (sub) {
+            case 64: return launch_nfilter<OP, 64, 3392, 4>(ctx, a, pa, tmp, F0, outK, n_out);
+            case 32: return launch_nfilter<OP, 32, 3392, 4>(ctx, a, pa, tmp, F0, outK, n_out);
+            case 16: return launch_nfilter<OP, 16, 3392, 4>(ctx, a, pa, tmp, F0, outK, n_out);
+            default: return launch_nfilter<OP, 8, 3392, 4>(ctx, a, pa, tmp, F0, outK, n_out);
+        }
+    }
+    switch (sub) {
+        case 64: return launch_nfilter<OP, 64, 4576, 3>(ctx, a, pa, tmp, F0, outK, n_out);
+        case 32: return launch_nfilter<OP, 32, 4576, 3>(ctx, a, pa, tmp, F0, outK, n_out);
+        case 16: return launch_nfilter<OP, 16, 4576, 3>(ctx, a, pa, tmp, F0, outK, n_out);
+        default: return launch_nfilter<OP, 8, 4576, 3>(ctx, a, pa, tmp, F0, outK, n_out);
+    }
+}
+
+}  // namespace
+
+bool ukm_nfilter_enabled() {
+    const char* e = getenv("UKM_NFILTER");
+    return !(e && e[0] == '0');
+}
+
+// keys[0] filtered by membership in keys[1..nf-1] (2..8 sorted duplicate-free device arrays): inter keeps the keys
+// found in every other array, diff the keys found in none.  outK capacity >= n[0].  *declined = true (nothing
+// written) when file 0 is so sparse against the others that streaming them is the wrong algorithm (the caller looks
+// file 0's keys up file by file instead).
+int ukm_nfilter(ukm_ctx* ctx, bool inter, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
+                bool* declined) {
+    *declined = false;
+    *n_out = 0;
+    if (nf < 2 || nf > NW_MAX) return ukm_fail(ctx, UKM_E_ARG, "nfilter: 2..8 inputs");
+    if (n[0] == 0) return UKM_OK;
+    NfArgs a;
+    NfPartArgs pa;
+    long long total = 0;
+    for (int f = 0; f < NW_MAX; ++f) {
+        a.F.k[f] = f < nf ? keys[f] : nullptr;
+        a.F.n[f] = f < nf ? (long long)n[f] : 0;
+        total += a.F.n[f];
+    }
+    a.F.nf = nf;
+    a.err = ctx->d_err;
+    a.null_mode = 0;
+#ifdef UKM_MEASURE  // measurement build only (make measure): the null modes produce no valid result
+    a.null_mode = nf_env_int("UKM_NFILTER_NULL", 0);
+#endif
+    pa.F = a.F;
+    pa.n0 = (long long)n[0];
+    // file-0 keys per warp so that a tile (8 warps) fits the slot with room for the spread of the segment sizes
+    const double ratio = (double)total / (double)n[0];
+    const double cap = nf_env_int("UKM_NFILTER_CFG", 0) == 1 ? 3392.0 : 4576.0;
+    int sub = 0;
+    for (int c = 64; c >= 8; c >>= 1)
+        if ((double)(NF_WARPS * c) * ratio <= 0.9 * cap) { sub = c; break; }
+    const int force = nf_env_int("UKM_NFILTER_SUB", 0);
+    if (force == 64 || force == 32 || force == 16 || force == 8) sub = force;
+    if (sub == 0) {
+        *declined = true;
+        return UKM_OK;
+    }
+    ukm_tmp tmp(ctx);
+    {
+        ukm_stat_scope st(ctx, inter ? "setop_inter_nway" : "setop_diff_nway", (double)total * 8.0);
+        if (inter) UKM_TRY(launch_nfilter_sub<NFOP_INTER>(ctx, sub, a, pa, tmp, keys[0], outK, n_out));
+        else UKM_TRY(launch_nfilter_sub<NFOP_DIFF>(ctx, sub, a, pa, tmp, keys[0], outK, n_out));
+    }
+    if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes += (double)*n_out * 8.0;
+    return UKM_OK;
+}

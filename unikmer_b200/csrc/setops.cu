@@ -1205,7 +1205,9 @@ int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags
     const size_t cap = in[0].n;
     DevSet bufs[2];
     int which = 0;
-    bool nway = !tax && ukm_nway_enabled() && nway_filter_enabled();
+    // keys-only runs: the single-pass filter over file-0 chunks (nfilter.cu, default) or the older rank-tiled one
+    const bool nfil = ukm_nfilter_enabled() && !nway_filter_enabled();
+    bool nway = !tax && (nfil || (ukm_nway_enabled() && nway_filter_enabled()));
     int i = 1;
     while (i < n_in) {
         if (op == OP_INTER) {
@@ -1232,7 +1234,9 @@ int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags
             }
             // worth it when file 0's share of a tile fits the hash table and it is not so sparse that looking its
             // keys up (setop_search_kernel) touches only a fraction of the other files
-            if (g >= 2 && ((cur.n * 3 <= total && cur.n * 64 >= largest) || nway_force())) {
+            // UKM_NFILTER_FORCE=1 (tests): take the chunk filter for any number of subjects and any size ratio
+            const bool nf_force = nfil && getenv("UKM_NFILTER_FORCE") && getenv("UKM_NFILTER_FORCE")[0] == '1';
+            if ((g >= 2 || (nf_force && g >= 1)) && ((cur.n * 3 <= total && cur.n * 64 >= largest) || nway_force() || nf_force)) {
                 DevSet G[NW_FANIN];
                 const uint64_t* ks[NW_FANIN];
                 size_t ns[NW_FANIN];
@@ -1247,7 +1251,8 @@ int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags
                 nxt = bufs[which];
                 bool fell_back = false;
                 size_t n_o = 0;
-                UKM_TRY(ukm_nway_filter(ctx, op == OP_INTER, ks, ns, g + 1, nxt.k, &n_o, &fell_back));
+                if (nfil) UKM_TRY(ukm_nfilter(ctx, op == OP_INTER, ks, ns, g + 1, nxt.k, &n_o, &fell_back));
+                else UKM_TRY(ukm_nway_filter(ctx, op == OP_INTER, ks, ns, g + 1, nxt.k, &n_o, &fell_back));
                 for (int q = 0; q < g; ++q) unstage_set(tmp, &in[idx[q]], &G[q]);
                 if (!fell_back) {
                     if (cur_is_input) {
