@@ -205,7 +205,7 @@ def test_nway_filter_misaligned_device_pointers(eng, monkeypatch):
 # ---------------------------------------------------------------------------------------
 # single-pass inter / diff over file-0 chunks (unikmer_b200/csrc/nfilter.cu, the default keys-only path)
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("cfg", ["0", "1"])
+@pytest.mark.parametrize("cfg", ["0", "1", "2"])
 @pytest.mark.parametrize("sub", ["0", "64", "32", "16", "8"])
 @pytest.mark.parametrize("nf", [2, 3, 5, 8])
 def test_nfilter_shapes(eng, cfg, sub, nf, monkeypatch):

@@ -51,6 +51,8 @@ struct ukm_ctx {
     std::map<std::string, ukm_stat_acc> stats;
     std::vector<ukm_pending_event> pending;
     std::vector<cudaEvent_t> event_pool;
+    // per-context (= per-device) kernel set-up: dynamic shared-memory opt-in done, resident CTAs per SM (-1 = not asked)
+    std::map<const void*, int> kcfg;
 };
 
 int ukm_fail(ukm_ctx* ctx, int code, const char* fmt, ...);
@@ -150,6 +152,34 @@ int ukm_nway_filter(ukm_ctx* ctx, bool inter, const uint64_t* const* keys, const
 bool ukm_nfilter_enabled();
 int ukm_nfilter(ukm_ctx* ctx, bool inter, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
                 bool* declined);
+
+// Opt `kern` in to `smem` bytes of dynamic shared memory on THIS context's device (the attribute is per device: a
+// process may own several GPUs) and, if threads > 0, report how many CTAs of it are resident per SM.  Cached per context.
+template <typename K>
+int ukm_kernel_config(ukm_ctx* ctx, K kern, size_t smem, int threads, int* ctas_per_sm) {
+    const void* key = reinterpret_cast<const void*>(kern);
+    auto it = ctx->kcfg.find(key);
+    if (it == ctx->kcfg.end()) {
+        if (smem > 48 * 1024) UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = -1;
+        if (threads > 0) {
+            UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem));
+            if (nb < 1) return ukm_fail(ctx, UKM_E_INTERNAL, "a persistent kernel does not fit on an SM of device %d", ctx->device);
+        }
+        it = ctx->kcfg.emplace(key, nb).first;
+    }
+    if (ctas_per_sm) *ctas_per_sm = it->second;
+    return UKM_OK;
+}
+// Persistent kernels whose CTAs wait on each other (grid-wide output-offset hand-off) are launched cooperatively: the
+// driver then guarantees that the whole grid is co-resident, whatever else shares the GPU (other contexts, MPS).
+template <typename K, typename A>
+int ukm_launch_coop(ukm_ctx* ctx, K kern, int grid, int threads, size_t smem, A& args) {
+    void* argv[] = {(void*)&args};
+    UKM_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(threads), argv, smem, ctx->stream));
+    ctx->launches++;
+    return UKM_OK;
+}
 
 static inline int ukm_grid_for(size_t work, int per_block, int sm_count, int max_per_sm = 32) {
     size_t g = (work + per_block - 1) / per_block;

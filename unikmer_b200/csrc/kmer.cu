@@ -440,12 +440,7 @@ int minimizer_select(ukm_ctx* ctx, const MinimizerGen& g, size_t n, uint64_t* d_
     if (g.w > MZ_WMAX) return ukm_dev_select(ctx, g, n, d_out, n_out, "minimizer_window", 8.0 * (double)n);
     const int num_tiles = (int)((n + MZ_TILE - 1) / MZ_TILE);
     const size_t smem = ((size_t)2 * MZ_TILE + (size_t)g.w + 1) * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {
-        UKM_CUDA(ctx, cudaFuncSetAttribute(minimizer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(((size_t)2 * MZ_TILE + MZ_WMAX + 1) * sizeof(uint64_t))));
-        configured = true;
-    }
+    UKM_TRY(ukm_kernel_config(ctx, minimizer_kernel, ((size_t)2 * MZ_TILE + MZ_WMAX + 1) * sizeof(uint64_t), 0, nullptr));
     ukm_tmp tmp(ctx);
     uint64_t* d_status = nullptr;
     UKM_TRY(tmp.alloc(&d_status, (size_t)num_tiles + 4));

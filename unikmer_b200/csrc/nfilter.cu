@@ -97,6 +97,7 @@ struct NfGeom {
     int off[NW_MAX];        // first element of the segment in the slot
     long long gpos[NW_MAX]; // global segment [gpos, gpos + gn)
     long long gn[NW_MAX];
+    int all_smem;           // every segment of the tile is in the slot (the fast path of the consumers)
 };
 
 struct NfSub {  // a warp's share of a segment
@@ -107,48 +108,48 @@ __device__ __forceinline__ int nf_slice_h(const uint64_t* g, long long start) {
     return (int)((reinterpret_cast<uintptr_t>(g + start) & 15u) >> 3);
 }
 
-// lower_bound of x in seg[0, n); *eq = the element there equals x.  The element at the answer is always the last
-// probe that was not below x (or the answer is n), so equality needs no extra load.
+// Branch-free searches with a fixed probe sequence (P = the largest power of two <= n, first probe at n - P, then
+// steps P/2 .. 1): ~8 instructions per probe and, when n is the same for every lane, no divergence.
+// number of elements of seg[0, n) below x
 template <typename IDX>
-__device__ __forceinline__ IDX nf_lower_bound(const uint64_t* seg, IDX n, uint64_t x, bool* eq) {
-    IDX lo = 0, len = n;
-    bool e = false;
-    while (len > 0) {
-        const IDX half = len >> 1;
-        const uint64_t v = seg[lo + half];
-        const bool lt = v < x;
-        e = lt ? e : (v == x);
-        lo = lt ? lo + half + 1 : lo;
-        len = lt ? len - half - 1 : half;
+__device__ __forceinline__ IDX nf_lower_bound(const uint64_t* seg, IDX n, uint64_t x) {
+    if (n <= 0) return 0;
+    const IDX P = sizeof(IDX) == 8 ? (IDX)(1ull << (63 - __clzll((long long)n))) : (IDX)(1u << (31 - __clz((int)n)));
+    IDX c = seg[n - P] < x ? n - P + 1 : 0;
+    for (IDX step = P >> 1; step > 0; step >>= 1)
+        if (seg[c + step - 1] < x) c += step;
+    return c;
+}
+// does x occur in seg[0, n)
+template <typename IDX>
+__device__ __forceinline__ bool nf_contains(const uint64_t* seg, IDX n, uint64_t x) {
+    if (n <= 0) return false;
+    const IDX P = sizeof(IDX) == 8 ? (IDX)(1ull << (63 - __clzll((long long)n))) : (IDX)(1u << (31 - __clz((int)n)));
+    IDX pos = seg[n - P] <= x ? n - P : 0;  // the last element <= x, if there is one
+    for (IDX step = P >> 1; step > 0; step >>= 1)
+        if (seg[pos + step] <= x) pos += step;
+    return seg[pos] == x;
+}
+// two keys against the same segment: two independent load chains, one loop
+__device__ __forceinline__ void nf_contains2(const uint64_t* seg, int n, uint64_t x0, uint64_t x1, bool* f0, bool* f1) {
+    if (n <= 0) {
+        *f0 = *f1 = false;
+        return;
     }
-    *eq = e;
-    return lo;
+    const int P = 1 << (31 - __clz(n));
+    const uint64_t v = seg[n - P];
+    int p0 = v <= x0 ? n - P : 0, p1 = v <= x1 ? n - P : 0;
+    for (int step = P >> 1; step > 0; step >>= 1) {
+        const uint64_t v0 = seg[p0 + step], v1 = seg[p1 + step];
+        if (v0 <= x0) p0 += step;
+        if (v1 <= x1) p1 += step;
+    }
+    *f0 = seg[p0] == x0;
+    *f1 = seg[p1] == x1;
 }
 
-// two keys against the same segment, probes interleaved (two independent load chains)
-__device__ __forceinline__ void nf_contains2(const uint64_t* seg, int n, uint64_t x0, uint64_t x1, bool* f0, bool* f1) {
-    int lo0 = 0, lo1 = 0;
-    bool e0 = false, e1 = false;
-    int len0 = n, len1 = n;
-    while (len0 > 0 || len1 > 0) {
-        const int h0 = len0 >> 1, h1 = len1 >> 1;
-        const uint64_t v0 = seg[lo0 + h0];  // reading seg[lo + 0] with len = 0 stays inside the slot (padding)
-        const uint64_t v1 = seg[lo1 + h1];
-        const bool lt0 = v0 < x0, lt1 = v1 < x1;
-        if (len0 > 0) {
-            e0 = lt0 ? e0 : (v0 == x0);
-            lo0 = lt0 ? lo0 + h0 + 1 : lo0;
-            len0 = lt0 ? len0 - h0 - 1 : h0;
-        }
-        if (len1 > 0) {
-            e1 = lt1 ? e1 : (v1 == x1);
-            lo1 = lt1 ? lo1 + h1 + 1 : lo1;
-            len1 = lt1 ? len1 - h1 - 1 : h1;
-        }
-    }
-    *f0 = e0;
-    *f1 = e1;
-}
+// floor(q / R) = (q * nf_inv[R]) >> 10 for q < 128, R in 1..7
+__constant__ unsigned short nf_inv[8] = {0, 1024, 512, 342, 256, 205, 171, 147};
 
 template <int SUB, int CAP>
 struct NfShape {
@@ -156,8 +157,306 @@ struct NfShape {
     static constexpr int SLOT_E = (CAP + 2 * NW_MAX + 2 + 1) & ~1;  // + per-segment alignment slack + read-past padding
 };
 
-template <int OP, int SUB, int CAP, int SLOTS>
-__global__ void __launch_bounds__(NF_THREADS, 2) nfilter_kernel(const NfArgs p) {
+// ---- one warp, SUB keys of file 0, every segment in shared memory: the fast path ---------------------------------
+// Shared-memory addresses are 32-bit (ld.shared with a register address, no generic-address translation).
+__device__ __forceinline__ uint64_t nf_lds(uint32_t a) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int nf_lg(int n) { return 32 - __clz((n > 1 ? n : 1) - 1); }  // smallest lg with 2^lg >= n
+
+// Searches with a warp-uniform, fully unrolled probe sequence: steps 2^(LG-1) .. 1 from the first element, every probe
+// address clamped to the last element (one VIADDMNMX), so any length 1 <= n <= 2^LG works with the same straight-line
+// code and lanes with different lengths never diverge: LDS / compare / predicated move, 5 instructions per probe.
+// `last` = shared address of the last element (of the first when n = 0: the caller masks the result).
+template <int LG>
+__device__ __forceinline__ uint32_t nf_last_le(uint32_t seg, uint32_t last, uint64_t x) {  // the last element <= x (seg if there is none)
+    uint32_t pp = seg;
+#pragma unroll
+    for (int k = LG - 1; k >= 0; --k) {
+        const uint32_t a = min(pp + (8u << k), last);
+        if (nf_lds(a) <= x) pp = a;
+    }
+    return pp;
+}
+template <int LG>
+__device__ __forceinline__ uint32_t nf_last_lt(uint32_t seg, uint32_t last, uint64_t x) {  // the last element < x (seg if there is none)
+    uint32_t pp = seg;
+#pragma unroll
+    for (int k = LG - 1; k >= 0; --k) {
+        const uint32_t a = min(pp + (8u << k), last);
+        if (nf_lds(a) < x) pp = a;
+    }
+    return pp;
+}
+__device__ __forceinline__ uint32_t nf_last_le_loop(uint32_t seg, uint32_t last, uint64_t x, int lg) {
+    uint32_t pp = seg;
+    for (uint32_t st = 8u << lg >> 1; st >= 8u; st >>= 1) {
+        const uint32_t a = min(pp + st, last);
+        if (nf_lds(a) <= x) pp = a;
+    }
+    return pp;
+}
+__device__ __forceinline__ uint32_t nf_last_lt_loop(uint32_t seg, uint32_t last, uint64_t x, int lg) {
+    uint32_t pp = seg;
+    for (uint32_t st = 8u << lg >> 1; st >= 8u; st >>= 1) {
+        const uint32_t a = min(pp + st, last);
+        if (nf_lds(a) < x) pp = a;
+    }
+    return pp;
+}
+// does x occur in the n sorted elements at shared address seg; lg = warp-uniform, 2^lg >= n of every lane
+__device__ __forceinline__ bool nf_find(uint32_t seg, int n, uint64_t x, int lg) {
+    const uint32_t last = seg + (unsigned)(n > 0 ? n - 1 : 0) * 8u;
+    uint32_t pp;
+    if (lg <= 6) pp = nf_last_le<6>(seg, last, x);
+    else if (lg == 7) pp = nf_last_le<7>(seg, last, x);
+    else pp = nf_last_le_loop(seg, last, x, lg);
+    return n > 0 && nf_lds(pp) == x;
+}
+// two keys, one segment: two independent load chains
+__device__ __forceinline__ void nf_find2(uint32_t seg, int n, uint64_t x0, uint64_t x1, int lg, bool* f0, bool* f1) {
+    const uint32_t last = seg + (unsigned)(n > 0 ? n - 1 : 0) * 8u;
+    uint32_t p0 = seg, p1 = seg;
+    if (lg <= 7) {
+#pragma unroll
+        for (int k = 6; k >= 0; --k) {
+            const uint32_t a0 = min(p0 + (8u << k), last), a1 = min(p1 + (8u << k), last);
+            const uint64_t v0 = nf_lds(a0), v1 = nf_lds(a1);
+            if (v0 <= x0) p0 = a0;
+            if (v1 <= x1) p1 = a1;
+        }
+    } else {
+        for (uint32_t st = 8u << lg >> 1; st >= 8u; st >>= 1) {
+            const uint32_t a0 = min(p0 + st, last), a1 = min(p1 + st, last);
+            const uint64_t v0 = nf_lds(a0), v1 = nf_lds(a1);
+            if (v0 <= x0) p0 = a0;
+            if (v1 <= x1) p1 = a1;
+        }
+    }
+    *f0 = n > 0 && nf_lds(p0) == x0;
+    *f1 = n > 0 && nf_lds(p1) == x1;
+}
+// number of elements below x
+__device__ __forceinline__ int nf_rank(uint32_t seg, int n, uint64_t x, int lg) {
+    const uint32_t last = seg + (unsigned)(n > 0 ? n - 1 : 0) * 8u;
+    uint32_t pp;
+    if (lg <= 10) pp = nf_last_lt<10>(seg, last, x);
+    else pp = nf_last_lt_loop(seg, last, x, lg);
+    return n > 0 ? (int)((pp - seg) >> 3) + (nf_lds(pp) < x ? 1 : 0) : 0;
+}
+
+template <int OP, int SUB>
+__device__ __forceinline__ unsigned long long nf_tile_fast(const uint64_t* slot, const NfGeom& g, uint8_t* list, int w, int cnt, int nf,
+                                                           unsigned lane, bool narrow_only) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = lanemask_lt();
+    const uint32_t slot_a = smem_u32(slot);
+    const int fq = (int)lane & 7;
+    // lane f (and f + 8, f + 16, f + 24): the tile's segment of file f
+    const int tN = fq < nf ? g.n[fq] : 0;
+    const uint32_t tseg = slot_a + (unsigned)(fq < nf ? g.off[fq] : 0) * 8u;
+    const uint32_t f0a = slot_a + (unsigned)(g.off[0] + w * SUB) * 8u;
+    // ---- narrow every segment to this warp's key range: lanes 1..7 the lower end, lanes 9..15 the upper end ----
+    uint32_t sub_a;  // lane f: shared address and length of file f's share
+    int sub_n;
+    {
+        const bool upper = lane >= 8;
+        const bool to_end = w * SUB + cnt >= g.n[0];  // the last warp of the tile takes the rest
+        const bool act = lane < 16 && fq >= 1 && fq < nf;
+        const int nn = act ? tN : 0;
+        const int lgmax = nf_lg(__reduce_max_sync(FULL, nn));
+        const uint64_t key = nf_lds(f0a + ((upper && !to_end) ? (unsigned)cnt * 8u : 0u));
+        int pos = nf_rank(tseg, (upper && to_end) ? 0 : nn, key, lgmax);
+        if (upper && to_end) pos = nn;
+        const int hi = __shfl_down_sync(FULL, pos, 8);
+        sub_a = tseg + (unsigned)pos * 8u;
+        sub_n = hi - pos;
+    }
+    unsigned alo = cnt >= 32 ? FULL : ((1u << cnt) - 1u);
+    unsigned ahi = (SUB > 32 && cnt > 32) ? (cnt >= 64 ? FULL : ((1u << (cnt - 32)) - 1u)) : 0u;
+    if (narrow_only) return ((unsigned long long)ahi << 32) | alo;
+    // ---- file 1: every key is still there, the lane takes its own keys ----
+    int f = 1;
+    {
+        const uint32_t seg = __shfl_sync(FULL, sub_a, 1);
+        const int n = __shfl_sync(FULL, sub_n, 1);
+        const int lgmax = nf_lg(n);
+        const uint64_t x0 = nf_lds(f0a + (lane < (unsigned)cnt ? lane : 0u) * 8u);
+        bool fd0, fd1 = false;
+        if (SUB > 32 && cnt > 32) {
+            const uint64_t x1 = nf_lds(f0a + ((int)lane + 32 < cnt ? lane + 32 : 0u) * 8u);
+            nf_find2(seg, n, x0, x1, lgmax, &fd0, &fd1);
+        } else {
+            fd0 = nf_find(seg, n, x0, lgmax);
+        }
+        alo &= ~__ballot_sync(FULL, OP == NFOP_INTER ? !fd0 : fd0);
+        if (SUB > 32) ahi &= ~__ballot_sync(FULL, OP == NFOP_INTER ? !fd1 : fd1);
+        f = 2;
+    }
+    // ---- the other files: survivors are re-listed every round; few survivors take several files per round ----
+    const uint32_t list_a = smem_u32(list);
+    while (f < nf && (alo | ahi)) {
+        const int a = __popc(alo) + __popc(ahi);
+        if (alo >> lane & 1u) list[__popc(alo & lt)] = (uint8_t)lane;
+        if (SUB > 32 && (ahi >> lane & 1u)) list[__popc(alo) + __popc(ahi & lt)] = (uint8_t)(lane + 32);
+        __syncwarp();
+        unsigned klo = 0, khi = 0;  // this lane's verdicts: survivors to drop
+        if (a > 32) {
+            // one file, two survivors per lane
+            const uint32_t seg = __shfl_sync(FULL, sub_a, f);
+            const int n = __shfl_sync(FULL, sub_n, f);
+            const int lgmax = nf_lg(n);
+            const bool v1 = (int)lane + 32 < a;
+            unsigned i0, i1;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(i0) : "r"(list_a + lane));
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(i1) : "r"(list_a + (v1 ? lane + 32 : lane)));
+            bool fd0, fd1;
+            nf_find2(seg, n, nf_lds(f0a + i0 * 8u), nf_lds(f0a + i1 * 8u), lgmax, &fd0, &fd1);
+            if (OP == NFOP_INTER ? !fd0 : fd0) {
+                if (i0 < 32) klo |= 1u << i0;
+                else khi |= 1u << (i0 - 32);
+            }
+            if (v1 && (OP == NFOP_INTER ? !fd1 : fd1)) {
+                if (i1 < 32) klo |= 1u << i1;
+                else khi |= 1u << (i1 - 32);
+            }
+            f += 1;
+        } else {
+            // (survivor, file) pairs: 1, 2, 4 or 8 files per round, whatever fills the warp
+            const int lgr = a > 16 ? 0 : a > 8 ? 1 : a > 4 ? 2 : 3;
+            const int si = (int)lane >> lgr, ff = f + ((int)lane & ((1 << lgr) - 1));
+            const bool valid = si < a && ff < nf;
+            const uint32_t seg = __shfl_sync(FULL, sub_a, ff & 7);
+            const int n_ff = __shfl_sync(FULL, sub_n, ff & 7);
+            const int n = valid ? n_ff : 0;
+            const int lgmax = nf_lg(__reduce_max_sync(FULL, n));
+            unsigned ix;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ix) : "r"(list_a + (valid ? si : 0)));
+            const bool fd = nf_find(seg, n, nf_lds(f0a + ix * 8u), lgmax);
+            if (valid && (OP == NFOP_INTER ? !fd : fd)) {
+                if (ix < 32) klo = 1u << ix;
+                else khi = 1u << (ix - 32);
+            }
+            f += 1 << lgr;
+        }
+        alo &= ~__reduce_or_sync(FULL, klo);
+        if (SUB > 32) ahi &= ~__reduce_or_sync(FULL, khi);
+        __syncwarp();  // the list is rewritten in the next round
+    }
+    return ((unsigned long long)ahi << 32) | alo;
+}
+
+// ---- the general path of a warp: some segment of the tile stayed in global memory ------------------------------
+template <int OP, int SUB>
+__device__ __noinline__ unsigned long long nf_tile_generic(const uint64_t* slot, const NfGeom& g, const uint64_t* const* s_fk, NfSub* sub,
+                                                           uint8_t* list, int w, int cnt, int nf, unsigned lane) {
+    const unsigned lt = lanemask_lt();
+    const int n0t = g.n[0];
+    unsigned alo = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+    unsigned ahi = (SUB > 32 && cnt > 32) ? (cnt >= 64 ? 0xffffffffu : ((1u << (cnt - 32)) - 1u)) : 0u;
+    const uint64_t* f0 = slot + g.off[0] + w * SUB;
+    // ---- narrow every segment to this warp's key range: lanes 0..7 the lower end, lanes 8..15 the upper end ----
+    {
+        const int f = (int)lane & 7;
+        const bool upper = lane >= 8;
+        long long pos = 0;
+        if (lane < 16 && f >= 1 && f < nf) {
+            const bool to_end = upper && (w * SUB + cnt >= n0t);  // the last warp of the tile takes the rest
+            const uint64_t key = upper ? (to_end ? 0 : f0[cnt]) : f0[0];
+            if (g.n[f] >= 0) pos = to_end ? g.n[f] : nf_lower_bound<int>(slot + g.off[f], g.n[f], key);
+            else pos = to_end ? g.gn[f] : nf_lower_bound<long long>(s_fk[f] + g.gpos[f], g.gn[f], key);
+        }
+        const long long hi = __shfl_down_sync(0xffffffffu, pos, 8);
+        if (lane < 8 && f >= 1 && f < nf) {
+            sub[f].lo = pos;
+            sub[f].n = hi - pos;
+        }
+    }
+    __syncwarp();
+    // ---- file by file with early exit; after the first file the survivors are re-listed every round ----
+    int f = 1;
+    bool first = true;
+    while (f < nf && (alo | ahi)) {
+        const int a = __popc(alo) + __popc(ahi);
+        const int R = nf - f;
+        unsigned klo = 0, khi = 0;  // this lane's verdicts: survivors to drop
+        if (first) {
+            // every key is still there: the lane takes its own two keys (no list)
+            first = false;
+            const long long slo = sub[f].lo, sn = sub[f].n;
+            const uint64_t x0 = f0[lane < (unsigned)cnt ? lane : 0];
+            const uint64_t x1 = f0[(SUB > 32 && (int)lane + 32 < cnt) ? lane + 32 : 0];
+            bool fd0, fd1 = false;
+            if (g.n[f] >= 0) {
+                const uint64_t* seg = slot + g.off[f] + (int)slo;
+                if (SUB > 32 && cnt > 32) nf_contains2(seg, (int)sn, x0, x1, &fd0, &fd1);
+                else fd0 = nf_contains<int>(seg, (int)sn, x0);
+            } else {
+                const uint64_t* seg = s_fk[f] + g.gpos[f] + slo;
+                fd0 = nf_contains<long long>(seg, sn, x0);
+                if (SUB > 32 && cnt > 32) fd1 = nf_contains<long long>(seg, sn, x1);
+            }
+            if (OP == NFOP_INTER ? !fd0 : fd0) klo = 1u << lane;
+            if (OP == NFOP_INTER ? !fd1 : fd1) khi = 1u << lane;
+            f += 1;
+        } else {
+            if (alo >> lane & 1u) list[__popc(alo & lt)] = (uint8_t)lane;
+            if (SUB > 32 && (ahi >> lane & 1u)) list[__popc(alo) + __popc(ahi & lt)] = (uint8_t)(lane + 32);
+            __syncwarp();
+            if (a * R > 64 || R == 1) {
+                // one file, every survivor
+                const long long slo = sub[f].lo, sn = sub[f].n;
+                const int i0 = list[lane < (unsigned)a ? lane : 0];
+                const int i1 = list[(int)lane + 32 < a ? lane + 32 : 0];
+                bool fd0, fd1 = false;
+                if (g.n[f] >= 0) {
+                    const uint64_t* seg = slot + g.off[f] + (int)slo;
+                    if (a > 32) nf_contains2(seg, (int)sn, f0[i0], f0[i1], &fd0, &fd1);
+                    else fd0 = nf_contains<int>(seg, (int)sn, f0[i0]);
+                } else {
+                    const uint64_t* seg = s_fk[f] + g.gpos[f] + slo;
+                    fd0 = nf_contains<long long>(seg, sn, f0[i0]);
+                    if (a > 32) fd1 = nf_contains<long long>(seg, sn, f0[i1]);
+                }
+                if ((int)lane < a && (OP == NFOP_INTER ? !fd0 : fd0)) {
+                    if (i0 < 32) klo |= 1u << i0;
+                    else khi |= 1u << (i0 - 32);
+                }
+                if ((int)lane + 32 < a && (OP == NFOP_INTER ? !fd1 : fd1)) {
+                    if (i1 < 32) klo |= 1u << i1;
+                    else khi |= 1u << (i1 - 32);
+                }
+                f += 1;
+            } else {
+                // the remaining files together: one (survivor, file) pair per lane and round (at most two rounds)
+                const int pairs = a * R;
+                const unsigned inv = nf_inv[R];
+                for (int qd = (int)lane; qd < pairs; qd += 32) {
+                    const int si = (int)(((unsigned)qd * inv) >> 10), ff = f + (qd - si * R);
+                    const int ix = list[si];
+                    const long long slo = sub[ff].lo, sn = sub[ff].n;
+                    bool fd;
+                    if (g.n[ff] >= 0) fd = nf_contains<int>(slot + g.off[ff] + (int)slo, (int)sn, f0[ix]);
+                    else fd = nf_contains<long long>(s_fk[ff] + g.gpos[ff] + slo, sn, f0[ix]);
+                    if (OP == NFOP_INTER ? !fd : fd) {
+                        if (ix < 32) klo |= 1u << ix;
+                        else khi |= 1u << (ix - 32);
+                    }
+                }
+                f = nf;
+            }
+        }
+        alo &= ~__reduce_or_sync(0xffffffffu, klo);
+        if (SUB > 32) ahi &= ~__reduce_or_sync(0xffffffffu, khi);
+        __syncwarp();  // the list is rewritten in the next round
+    }
+    return ((unsigned long long)ahi << 32) | alo;
+}
+
+template <int OP, int SUB, int CAP, int SLOTS, int MINB>
+__global__ void __launch_bounds__(NF_THREADS, MINB) nfilter_kernel(const NfArgs p) {
     using SH = NfShape<SUB, CAP>;
     extern __shared__ __align__(16) unsigned char nf_smem[];
     uint64_t* s_slots = reinterpret_cast<uint64_t*>(nf_smem);  // SLOTS * SLOT_E
@@ -183,26 +482,29 @@ __global__ void __launch_bounds__(NF_THREADS, 2) nfilter_kernel(const NfArgs p) 
     const unsigned lane = lane_id();
 
     if (threadIdx.x < 32) {
-        // ================= loader warp: lane f owns file f =================
-        const bool mine = (int)lane < nf;
-        const uint64_t* fk = mine ? s_fk[lane] : nullptr;
-        // software pipeline: cut positions two tiles ahead, the unaligned head / tail elements one tile ahead, so
-        // that no global-memory latency sits between two tiles of the loader
+        // ================= loader warp: four tiles per batch, lane = 8 * (tile in batch) + file =================
+        // The cut positions of a batch are fetched two batches ahead and the unaligned head / tail elements one batch
+        // ahead, so the global-memory latency of that bookkeeping is paid once per four tiles and never between tiles.
+        const int q = (int)lane >> 3, f = (int)lane & 7;
+        const bool mine = f < nf;
+        const uint64_t* fk = mine ? s_fk[f] : nullptr;
+        const int n_batches = (n_my + 3) >> 2;
         long long lo_a = 0, nn_a = 0, lo_b = 0, nn_b = 0;
         uint64_t hv_a = 0, tv_a = 0;
-        auto fetch_bounds = [&](int li, long long* lo, long long* nn) {
+        auto fetch_bounds = [&](int b, long long* lo, long long* nn) {
             *lo = 0;
             *nn = 0;
+            const int li = b * 4 + q;
             if (mine && li < n_my) {
                 const int t = (int)blockIdx.x + li * G;
-                *lo = p.bounds[t].pos[lane];
-                *nn = p.bounds[t + 1].pos[lane] - *lo;
+                *lo = p.bounds[t].pos[f];
+                *nn = p.bounds[t + 1].pos[f] - *lo;
             }
         };
         auto fetch_edges = [&](long long lo, long long nn, uint64_t* hv, uint64_t* tv) {
             *hv = 0;
             *tv = 0;
-            if (mine && nn > 0 && nn <= CAP) {
+            if (mine && nn > 0 && nn <= CAP && p.null_mode != 2) {
                 *hv = fk[lo];
                 *tv = fk[lo + nn - 1];
             }
@@ -210,62 +512,70 @@ __global__ void __launch_bounds__(NF_THREADS, 2) nfilter_kernel(const NfArgs p) 
         fetch_bounds(0, &lo_a, &nn_a);
         fetch_edges(lo_a, nn_a, &hv_a, &tv_a);
         fetch_bounds(1, &lo_b, &nn_b);
-        for (int li = 0; li < n_my; ++li) {
-            const int s = li % SLOTS, u = li / SLOTS;
+        for (int b = 0; b < n_batches; ++b) {
             uint64_t hv_b, tv_b;
             long long lo_c, nn_c;
-            fetch_edges(lo_b, nn_b, &hv_b, &tv_b);  // in flight until the next iteration uses them
-            fetch_bounds(li + 2, &lo_c, &nn_c);
-            if (u > 0 && !mbar_wait(&empty_bar[s], (unsigned)(u - 1) & 1u)) {
-                if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
-            }
+            fetch_edges(lo_b, nn_b, &hv_b, &tv_b);  // in flight while this batch is issued
+            fetch_bounds(b + 2, &lo_c, &nn_c);
             const long long lo = lo_a, nn = nn_a;
             if (__any_sync(0xffffffffu, nn < 0)) {  // cannot happen: the cuts of a sorted file are monotone
                 if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
             }
-            // greedy layout in file order: a segment goes into the slot if it still fits, else it stays in global memory
             const int h = (mine && nn > 0) ? nf_slice_h(fk, lo) : 0;
             const int padded = (mine && nn > 0 && nn <= CAP) ? (int)((h + nn + 1) & ~1ll) : 0;
-            int base = 0, my_base = 0;
-            bool my_fit = false;
-#pragma unroll
-            for (int f = 0; f < NW_MAX; ++f) {
-                const int pf = __shfl_sync(0xffffffffu, padded, f);
-                const long long nnf = __shfl_sync(0xffffffffu, nn, f);
-                const bool fit = nnf <= 0 || (nnf <= CAP && base + pf <= CAP);
-                if ((int)lane == f) {
-                    my_fit = fit;
-                    my_base = base;
+            for (int qq = 0; qq < 4; ++qq) {
+                const int li = b * 4 + qq;
+                if (li >= n_my) break;
+                const int s = li % SLOTS, u = li / SLOTS;
+                if (u > 0 && !mbar_wait(&empty_bar[s], (unsigned)(u - 1) & 1u)) {
+                    if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
                 }
-                if (fit) base += pf;
-            }
-            uint64_t* slot = s_slots + (size_t)s * SH::SLOT_E;
-            const int n = my_fit ? (int)(nn > 0 ? nn : 0) : 0;
-            int head = 0, body = 0;
-            if (n > 0) {
-                head = h ? 1 : 0;
-                body = (n - head) & ~1;
-                if (head) slot[my_base + h] = hv_a;
-                if (head + body < n) slot[my_base + h + n - 1] = tv_a;
-            }
-            if (p.null_mode == 2) {  // measurement aid: the barrier ring alone
-                if (mine) s_geom[s].n[lane] = 0;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[s]);
-            } else {
-            unsigned bytes = (unsigned)body * 8u;
+                // greedy layout in file order: a segment goes into the slot if it still fits, else it stays in global memory
+                int base = 0, my_base = 0;
+                bool my_fit = false;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
-            if (mine) {
-                s_geom[s].n[lane] = my_fit ? n : -1;
-                s_geom[s].off[lane] = my_base + h;
-                s_geom[s].gpos[lane] = lo;
-                s_geom[s].gn[lane] = nn;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_expect_tx(&full_bar[s], bytes);  // arrive (release: plain stores + geometry) + tx count
-            __syncwarp();
-            if (body) tma_load_1d(slot + my_base + h + head, fk + lo + head, (unsigned)body * 8u, &full_bar[s]);
+                for (int ff = 0; ff < NW_MAX; ++ff) {
+                    const int src = qq * 8 + ff;
+                    const int pf = __shfl_sync(0xffffffffu, padded, src);
+                    const long long nnf = __shfl_sync(0xffffffffu, nn, src);
+                    const bool fit = nnf <= 0 || (nnf <= CAP && base + pf <= CAP);
+                    if ((int)lane == src) {
+                        my_fit = fit;
+                        my_base = base;
+                    }
+                    if (fit) base += pf;
+                }
+                const bool act = q == qq && mine;
+                uint64_t* slot = s_slots + (size_t)s * SH::SLOT_E;
+                if (p.null_mode == 2) {  // measurement aid: the barrier ring alone
+                    if (act) s_geom[s].n[f] = 0;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);
+                    continue;
+                }
+                const int n = (act && my_fit && nn > 0) ? (int)nn : 0;
+                int head = 0, body = 0;
+                if (n > 0) {
+                    head = h ? 1 : 0;
+                    body = (n - head) & ~1;
+                    if (head) slot[my_base + h] = hv_a;
+                    if (head + body < n) slot[my_base + h + n - 1] = tv_a;
+                }
+                unsigned bytes = (unsigned)body * 8u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
+                const bool all_fit = __all_sync(0xffffffffu, q != qq || !mine || my_fit);
+                if (lane == 0) s_geom[s].all_smem = all_fit ? 1 : 0;
+                if (act) {
+                    s_geom[s].n[f] = my_fit ? n : -1;
+                    s_geom[s].off[f] = my_base + h;
+                    s_geom[s].gpos[f] = lo;
+                    s_geom[s].gn[f] = nn;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_expect_tx(&full_bar[s], bytes);  // arrive (release: plain stores + geometry) + tx count
+                __syncwarp();
+                if (body) tma_load_1d(slot + my_base + h + head, fk + lo + head, (unsigned)body * 8u, &full_bar[s]);
             }
             lo_a = lo_b; nn_a = nn_b; hv_a = hv_b; tv_a = tv_b;
             lo_b = lo_c; nn_b = nn_c;
@@ -275,8 +585,6 @@ __global__ void __launch_bounds__(NF_THREADS, 2) nfilter_kernel(const NfArgs p) 
 
     // ================= consumer warps: SUB keys of file 0 each, no block-wide synchronisation =================
     const int w = ((int)threadIdx.x >> 5) - 1;
-    uint8_t* list = s_list[w];
-    NfSub* sub = s_sub[w];
     for (int i = 0; i < n_my; ++i) {
         const int s = i % SLOTS, u = i / SLOTS;
         const int tile = (int)blockIdx.x + i * G;
@@ -285,90 +593,13 @@ __global__ void __launch_bounds__(NF_THREADS, 2) nfilter_kernel(const NfArgs p) 
             if (lane == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
         }
         const NfGeom& g = s_geom[s];
-        const int n0t = g.n[0];
-        int cnt = n0t - w * SUB;
+        int cnt = g.n[0] - w * SUB;
         cnt = cnt < 0 ? 0 : (cnt > SUB ? SUB : cnt);
-        unsigned long long alive = cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull);
-        const uint64_t* f0 = slot + g.off[0] + w * SUB;
-        if (cnt > 0 && p.null_mode != 1 && p.null_mode != 2) {
-            // ---- narrow every segment to this warp's key range: lanes 0..7 the lower end, lanes 8..15 the upper end ----
-            {
-                const int f = (int)lane & 7;
-                const bool upper = lane >= 8;
-                long long pos = 0;
-                if (lane < 16 && f >= 1 && f < nf) {
-                    const bool to_end = upper && (w * SUB + cnt >= n0t);  // the last warp of the tile takes the rest
-                    const uint64_t key = upper ? (to_end ? 0 : f0[cnt]) : f0[0];
-                    bool eq;
-                    if (g.n[f] >= 0) {
-                        pos = to_end ? g.n[f] : nf_lower_bound<int>(slot + g.off[f], g.n[f], key, &eq);
-                    } else {
-                        pos = to_end ? g.gn[f] : nf_lower_bound<long long>(s_fk[f] + g.gpos[f], g.gn[f], key, &eq);
-                    }
-                }
-                const long long hi = __shfl_down_sync(0xffffffffu, pos, 8);
-                if (lane < 8 && f >= 1 && f < nf) {
-                    sub[f].lo = pos;
-                    sub[f].n = hi - pos;
-                }
-            }
-            __syncwarp();
-            // ---- file by file with early exit; survivors are re-listed after every file ----
-            int f = p.null_mode == 3 ? nf : 1;
-            while (f < nf && alive) {
-                const int a = __popcll(alive);
-                const int R = nf - f;
-                if (alive >> lane & 1ull) list[__popcll(alive & ((1ull << lane) - 1ull))] = (uint8_t)lane;
-                if (SUB > 32 && (alive >> (lane + 32) & 1ull)) list[__popcll(alive & ((1ull << (lane + 32)) - 1ull))] = (uint8_t)(lane + 32);
-                __syncwarp();
-                unsigned long long kill = 0;
-                if (a * R > 64 || R == 1) {
-                    // one file, every survivor
-                    const long long slo = sub[f].lo, sn = sub[f].n;
-                    if (g.n[f] >= 0) {
-                        const uint64_t* seg = slot + g.off[f] + (int)slo;
-                        const int i0 = lane < (unsigned)a ? list[lane] : 0;
-                        if (a > 32) {
-                            const bool v1 = (int)lane + 32 < a;
-                            const int i1 = v1 ? list[lane + 32] : i0;
-                            bool fd0, fd1;
-                            nf_contains2(seg, (int)sn, f0[i0], f0[i1], &fd0, &fd1);
-                            if (OP == NFOP_INTER ? !fd0 : fd0) kill |= 1ull << i0;
-                            if (v1 && (OP == NFOP_INTER ? !fd1 : fd1)) kill |= 1ull << i1;
-                        } else if ((int)lane < a) {
-                            bool fd;
-                            nf_lower_bound<int>(seg, (int)sn, f0[i0], &fd);
-                            if (OP == NFOP_INTER ? !fd : fd) kill |= 1ull << i0;
-                        }
-                    } else {
-                        const uint64_t* seg = s_fk[f] + g.gpos[f] + slo;
-                        for (int j = (int)lane; j < a; j += 32) {
-                            const int ix = list[j];
-                            bool fd;
-                            nf_lower_bound<long long>(seg, sn, f0[ix], &fd);
-                            if (OP == NFOP_INTER ? !fd : fd) kill |= 1ull << ix;
-                        }
-                    }
-                    f += 1;
-                } else {
-                    // the remaining files together: one (survivor, file) pair per lane and round
-                    const int pairs = a * R;
-                    for (int q = (int)lane; q < pairs; q += 32) {
-                        const int si = q / R, ff = f + (q - si * R);
-                        const int ix = list[si];
-                        const long long slo = sub[ff].lo, sn = sub[ff].n;
-                        bool fd;
-                        if (g.n[ff] >= 0) nf_lower_bound<int>(slot + g.off[ff] + (int)slo, (int)sn, f0[ix], &fd);
-                        else nf_lower_bound<long long>(s_fk[ff] + g.gpos[ff] + slo, sn, f0[ix], &fd);
-                        if (OP == NFOP_INTER ? !fd : fd) kill |= 1ull << ix;
-                    }
-                    f = nf;
-                }
-                const unsigned klo = __reduce_or_sync(0xffffffffu, (unsigned)kill);
-                const unsigned khi = SUB > 32 ? __reduce_or_sync(0xffffffffu, (unsigned)(kill >> 32)) : 0u;
-                alive &= ~(((unsigned long long)khi << 32) | klo);
-                __syncwarp();  // the list is rewritten in the next round
-            }
+        unsigned long long alive = 0;
+        if (cnt > 0 && p.null_mode != 2) {
+            if (p.null_mode == 1) alive = cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull);
+            else if (g.all_smem) alive = nf_tile_fast<OP, SUB>(slot, g, s_list[w], w, cnt, nf, lane, p.null_mode == 3);
+            else alive = nf_tile_generic<OP, SUB>(slot, g, s_fk, s_sub[w], s_list[w], w, cnt, nf, lane);
         }
         if (lane == 0) p.masks[(size_t)tile * NF_WARPS + w] = alive;
         __syncwarp();  // every lane is past its reads of the slot
@@ -497,16 +728,13 @@ int nf_env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <int OP, int SUB, int CAP, int SLOTS>
+template <int OP, int SUB, int CAP, int SLOTS, int MINB>
 int launch_nfilter(ukm_ctx* ctx, NfArgs a, NfPartArgs pa, ukm_tmp& tmp, const uint64_t* F0, uint64_t* outK, size_t* n_out) {
     using SH = NfShape<SUB, CAP>;
     constexpr size_t smem = (size_t)SLOTS * SH::SLOT_E * 8;
-    auto kern = nfilter_kernel<OP, SUB, CAP, SLOTS>;
-    // per launch: the attribute belongs to the device of the current context (one process may own several GPUs)
-    UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = nfilter_kernel<OP, SUB, CAP, SLOTS, MINB>;
     int per_sm = 0;
-    UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NF_THREADS, smem));
-    if (per_sm < 1) return ukm_fail(ctx, UKM_E_INTERNAL, "nfilter_kernel does not fit on an SM");
+    UKM_TRY(ukm_kernel_config(ctx, kern, smem, NF_THREADS, &per_sm));
     pa.M = SH::M;
     const int num_tiles = (int)((pa.n0 + SH::M - 1) / SH::M);
     pa.num_tiles = num_tiles;
@@ -550,22 +778,20 @@ int launch_nfilter(ukm_ctx* ctx, NfArgs a, NfPartArgs pa, ukm_tmp& tmp, const ui
 template <int OP>
 int launch_nfilter_sub(ukm_ctx* ctx, int sub, const NfArgs& a, const NfPartArgs& pa, ukm_tmp& tmp, const uint64_t* F0, uint64_t* outK,
                        size_t* n_out) {
-    // slot capacity x ring depth: 3 x 36 KB (two CTAs per SM); UKM_NFILTER_CFG=1: 4 x 27 KB for A/B runs
+    // slot capacity x ring depth x CTAs per SM: 2 x 36 KB x 3 (default: C3 inter 10.0 ms on B200); UKM_NFILTER_CFG = 1: 4 x 27 KB x 2
+    // (19.5 ms: tiles of 256 file-0 keys), 2: 3 x 36 KB x 2 (11.4 ms: 16 instead of 24 consumer warps per SM) -- A/B runs
     const int cfg = nf_env_int("UKM_NFILTER_CFG", 0);
-    if (cfg == 1) {
-        switch (sub) {
-            case 64: return launch_nfilter<OP, 64, 3392, 4>(ctx, a, pa, tmp, F0, outK, n_out);
-            case 32: return launch_nfilter<OP, 32, 3392, 4>(ctx, a, pa, tmp, F0, outK, n_out);
-            case 16: return launch_nfilter<OP, 16, 3392, 4>(ctx, a, pa, tmp, F0, outK, n_out);
-            default: return launch_nfilter<OP, 8, 3392, 4>(ctx, a, pa, tmp, F0, outK, n_out);
-        }
+#define NF_LAUNCH(CAP, SLOTS, MINB)                                                                                   \
+    switch (sub) {                                                                                                    \
+        case 64: return launch_nfilter<OP, 64, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out);                    \
+        case 32: return launch_nfilter<OP, 32, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out);                    \
+        case 16: return launch_nfilter<OP, 16, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out);                    \
+        default: return launch_nfilter<OP, 8, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out);                     \
     }
-    switch (sub) {
-        case 64: return launch_nfilter<OP, 64, 4576, 3>(ctx, a, pa, tmp, F0, outK, n_out);
-        case 32: return launch_nfilter<OP, 32, 4576, 3>(ctx, a, pa, tmp, F0, outK, n_out);
-        case 16: return launch_nfilter<OP, 16, 4576, 3>(ctx, a, pa, tmp, F0, outK, n_out);
-        default: return launch_nfilter<OP, 8, 4576, 3>(ctx, a, pa, tmp, F0, outK, n_out);
-    }
+    if (cfg == 1) { NF_LAUNCH(3392, 4, 2) }
+    if (cfg == 2) { NF_LAUNCH(4576, 3, 2) }
+    NF_LAUNCH(4576, 2, 3)
+#undef NF_LAUNCH
 }
 
 }  // namespace

@@ -469,14 +469,8 @@ int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_
     using SH = NwShape<NWAY, NT, VT>;
     constexpr size_t smem = ((size_t)SLOTS * SH::SLOT_E + nw_x_elems<OP, NWAY, NT, VT>()) * 8;
     auto kern = nway_kernel<OP, NWAY, NT, VT, SLOTS, MINB, DEFER>;
-    static int ctas_per_sm = 0;  // per instantiation
-    if (ctas_per_sm == 0) {
-        UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int nb = 0;
-        UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT + NWK_AUX, smem));
-        if (nb < 1) return ukm_fail(ctx, UKM_E_INTERNAL, "nway_kernel does not fit on an SM");
-        ctas_per_sm = nb;
-    }
+    int ctas_per_sm = 0;
+    UKM_TRY(ukm_kernel_config(ctx, kern, smem, NT + NWK_AUX, &ctas_per_sm));
     // ---- partition: tiles of ~TILE elements summed over all files ----
     pa.tile = SH::TILE;
     pa.tol = SH::TILE / 32;
@@ -515,8 +509,7 @@ int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_
     int grid = ctas_per_sm * ctx->sm_count;
     if (grid > NWK_MAX_GRID) grid = NWK_MAX_GRID;
     if (grid > num_tiles) grid = num_tiles;
-    kern<<<grid, NT + NWK_AUX, smem, ctx->stream>>>(a);
-    UKM_LAUNCHED(ctx);
+    UKM_TRY(ukm_launch_coop(ctx, kern, grid, NT + NWK_AUX, smem, a));  // co-residency guaranteed by the driver
     UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     tmp.free_now(d_bounds);

@@ -888,11 +888,7 @@ template <int OP, bool TAX, bool CNT>
 int launch_setop_v(ukm_ctx* ctx, const SetopArgs& a) {
     constexpr size_t smem = setop_smem(TAX, CNT);
     auto kern = setop_kernel<OP, TAX, CNT>;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    UKM_TRY(ukm_kernel_config(ctx, kern, smem, 0, nullptr));
     kern<<<a.num_tiles, SO_THREADS, smem, ctx->stream>>>(a);
     UKM_LAUNCHED(ctx);
     return UKM_OK;
@@ -919,11 +915,7 @@ template <int OP, int VT>
 int launch_fast_v(ukm_ctx* ctx, const SetopArgs& a) {
     constexpr size_t smem = (size_t)2 * (SO_THREADS * VT + 8) * 8;
     auto kern = setop_fast_kernel<OP, VT>;
-    static bool configured = false;
-    if (!configured) {
-        UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    UKM_TRY(ukm_kernel_config(ctx, kern, smem, 0, nullptr));
     kern<<<a.num_tiles, SO_THREADS, smem, ctx->stream>>>(a);
     UKM_LAUNCHED(ctx);
     return UKM_OK;
@@ -943,21 +935,13 @@ template <int OP, int NT, int VT, int SLOTS, int MINB>
 int launch_pipe_v(ukm_ctx* ctx, SetopArgs a) {
     constexpr size_t smem = (size_t)SLOTS * (NT * VT + 8) * 8;
     auto kern = setop_pipe_kernel<OP, NT, VT, SLOTS, MINB>;
-    static int ctas_per_sm = 0;  // per instantiation
-    if (ctas_per_sm == 0) {
-        UKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int nb = 0;
-        UKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT + PIPE_AUX, smem));
-        if (nb < 1) return ukm_fail(ctx, UKM_E_INTERNAL, "setop_pipe_kernel does not fit on an SM");
-        ctas_per_sm = nb;
-    }
+    int ctas_per_sm = 0;
+    UKM_TRY(ukm_kernel_config(ctx, kern, smem, NT + PIPE_AUX, &ctas_per_sm));
     // persistent grid: every CTA must be resident (tiles are chained in index order)
     int grid = ctas_per_sm * ctx->sm_count;
     if (grid > PIPE_MAX_GRID) grid = PIPE_MAX_GRID;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    kern<<<grid, NT + PIPE_AUX, smem, ctx->stream>>>(a);
-    UKM_LAUNCHED(ctx);
-    return UKM_OK;
+    return ukm_launch_coop(ctx, kern, grid, NT + PIPE_AUX, smem, a);  // co-residency guaranteed by the driver
 }
 
 template <int NT, int VT, int SLOTS, int MINB>
