@@ -22,10 +22,14 @@ def exp_union(files):
     return np.unique(np.concatenate([np.asarray(f, dtype=U64) for f in files]))
 
 
-@pytest.mark.parametrize("cfg", ["0", "1", "2", "3", "4"])
+@pytest.mark.parametrize("cfg", ["rows", "0", "1", "2", "3", "4"])
 @pytest.mark.parametrize("nf", [2, 3, 4, 5, 7, 8])
 def test_nway_union_shapes(eng, cfg, nf, monkeypatch):
-    monkeypatch.setenv("UKM_NWAY_CFG", cfg)
+    """cfg "rows": the row-based kernel (nunion.cu, opt-in); "0".."4": the tile shapes of the sequential-walk kernel."""
+    if cfg == "rows":
+        monkeypatch.setenv("UKM_NUNION", "1")
+    else:
+        monkeypatch.setenv("UKM_NWAY_CFG", cfg)
     monkeypatch.setenv("UKM_NWAY_FORCE", "1")  # two sets go to the two-way pipeline by default
     for N in (3_000, 250_000, 2_500_000):
         files = member_files(N, nf)
@@ -49,7 +53,10 @@ def test_nway_union_matches_two_way_tree(eng, monkeypatch):
     same(a, oracle.union(files)[0], "nway vs oracle")
 
 
-def test_nway_union_distributions(eng):
+@pytest.mark.parametrize("kernel", ["rows", "walk"])
+def test_nway_union_distributions(eng, kernel, monkeypatch):
+    if kernel == "rows":
+        monkeypatch.setenv("UKM_NUNION", "1")
     r = rng(11)
     cases = {}
     # full 64-bit range with both extremes present in several files
@@ -80,8 +87,11 @@ def test_nway_union_distributions(eng):
         same(eng.union(files)[0], exp_union(files), f"union {name}")
 
 
-def test_nway_union_misaligned_device_pointers(eng):
+@pytest.mark.parametrize("kernel", ["rows", "walk"])
+def test_nway_union_misaligned_device_pointers(eng, kernel, monkeypatch):
     import torch
+    if kernel == "rows":
+        monkeypatch.setenv("UKM_NUNION", "1")
     files = member_files(700_000, 8)
     d = [torch.from_numpy(f.view(np.int64)).cuda()[(i % 2):] for i, f in enumerate(files)]  # 8 mod 16 pointers on odd files
     exp = exp_union([x.cpu().numpy().view(U64) for x in d])

@@ -19,3 +19,16 @@ def test_nway_host_model(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "nway model ok" in out.stdout
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_rows_host_model(tmp_path):
+    """The row-based union (unikmer_b200/csrc/rows_core.cuh, nunion.cu): pair tables with reversed / congruent runs,
+    merge-path splits in padded rows, rotated gather + bitonic merge network, 8 warps x 31 rows per level -- replayed on
+    the CPU against std::set_union, with the bank-conflict-free claim of the gather checked round by round."""
+    exe = tmp_path / "rows_model"
+    src = os.path.join(ROOT, "tests", "host", "rows_model.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", src, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "rows model ok" in out.stdout and " 0 with a bank conflict" in out.stdout

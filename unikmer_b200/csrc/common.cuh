@@ -148,6 +148,10 @@ int ukm_nway_union(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, i
 int ukm_nway_filter(ukm_ctx* ctx, bool inter, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,
                     bool* fell_back);
 
+// the same union with row-based merge levels (nunion.cu: conflict-free gathers + bitonic merge networks in registers)
+bool ukm_nunion_enabled();
+int ukm_nunion(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out, bool* fell_back);
+
 // single-pass N-way inter / diff over file-0 chunks (nfilter.cu): keys[0] filtered by membership in keys[1..nf-1]
 bool ukm_nfilter_enabled();
 int ukm_nfilter(ukm_ctx* ctx, bool inter, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out,

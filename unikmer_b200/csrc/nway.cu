@@ -21,6 +21,9 @@
 #include "common.cuh"
 #include "nway_core.cuh"
 
+int ukm_nway_partition(ukm_ctx* ctx, const NwFiles& F, long long total, int tile, int cap, ukm_tmp& tmp, NwBound** d_bounds_out,
+                       uint64_t** d_status_out, int* num_tiles_out, bool* bad);
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------------
@@ -472,36 +475,12 @@ int launch_nway(ukm_ctx* ctx, NwArgs a, NwPartArgs pa, ukm_tmp& tmp, bool* fell_
     int ctas_per_sm = 0;
     UKM_TRY(ukm_kernel_config(ctx, kern, smem, NT + NWK_AUX, &ctas_per_sm));
     // ---- partition: tiles of ~TILE elements summed over all files ----
-    pa.tile = SH::TILE;
-    pa.tol = SH::TILE / 32;
-    const int num_tiles = (int)((pa.total + SH::TILE - 1) / SH::TILE);
-    pa.num_tiles = num_tiles;
     NwBound* d_bounds = nullptr;
     uint64_t* d_status = nullptr;
-    UKM_TRY(tmp.alloc(&d_bounds, (size_t)num_tiles + 1));
-    UKM_TRY(tmp.alloc(&d_status, (size_t)num_tiles + 4));
-    // output total and the check words live in the tail of the status allocation (zeroed together)
+    int num_tiles = 0;
+    UKM_TRY(ukm_nway_partition(ctx, pa.F, pa.total, SH::TILE, SH::CAP, tmp, &d_bounds, &d_status, &num_tiles, fell_back));
+    if (*fell_back) return UKM_OK;  // some key occurs far too often for a tile: inputs are not duplicate-free
     unsigned long long* d_total = reinterpret_cast<unsigned long long*>(d_status + num_tiles);
-    int* d_info = reinterpret_cast<int*>(d_status + num_tiles + 1);
-    UKM_CUDA(ctx, cudaMemsetAsync(d_status, 0, ((size_t)num_tiles + 4) * sizeof(uint64_t), ctx->stream));
-    {
-        constexpr int S0 = 64, S1 = 8;
-        const int n0 = num_tiles / S0 + 1, n1 = num_tiles / S1 + 1;
-        nway_partition_kernel<<<(n0 + 63) / 64, 64, 0, ctx->stream>>>(pa, d_bounds, S0, 0);
-        UKM_LAUNCHED(ctx);
-        nway_partition_kernel<<<(n1 + 63) / 64, 64, 0, ctx->stream>>>(pa, d_bounds, S1, S0);
-        UKM_LAUNCHED(ctx);
-        nway_partition_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(pa, d_bounds, 1, S1);
-        UKM_LAUNCHED(ctx);
-    }
-    nway_check_kernel<<<(num_tiles + 127) / 128, 128, 0, ctx->stream>>>(d_bounds, num_tiles, SH::CAP, d_info);
-    UKM_LAUNCHED(ctx);
-    UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_info, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (reinterpret_cast<int*>(ctx->h_scratch)[0] != 0) {
-        *fell_back = true;  // some key occurs far too often for a tile: inputs are not duplicate-free
-        return UKM_OK;
-    }
     a.bounds = d_bounds;
     a.status = d_status;
     a.total_out = d_total;
@@ -582,6 +561,46 @@ int nway_run(ukm_ctx* ctx, int op, const char* stat_name, const uint64_t* const*
 }
 
 }  // namespace
+
+// Tiles of ~tile elements summed over all files (boundaries exact to +- tile / 32, never above `cap`): the three-level
+// multi-sequence selection above + the capacity check.  Allocates the boundaries and a zeroed status array of
+// num_tiles + 4 words (tile counts, then the output total, then the check words).  *bad = the inputs cannot be tiled.
+// Shared with the row-based union (nunion.cu).
+int ukm_nway_partition(ukm_ctx* ctx, const NwFiles& F, long long total, int tile, int cap, ukm_tmp& tmp, NwBound** d_bounds_out,
+                       uint64_t** d_status_out, int* num_tiles_out, bool* bad) {
+    NwPartArgs pa;
+    pa.F = F;
+    pa.total = total;
+    pa.tile = tile;
+    pa.tol = tile / 32;
+    const int num_tiles = (int)((total + tile - 1) / tile);
+    pa.num_tiles = num_tiles;
+    NwBound* d_bounds = nullptr;
+    uint64_t* d_status = nullptr;
+    UKM_TRY(tmp.alloc(&d_bounds, (size_t)num_tiles + 1));
+    UKM_TRY(tmp.alloc(&d_status, (size_t)num_tiles + 4));
+    int* d_info = reinterpret_cast<int*>(d_status + num_tiles + 1);
+    UKM_CUDA(ctx, cudaMemsetAsync(d_status, 0, ((size_t)num_tiles + 4) * sizeof(uint64_t), ctx->stream));
+    {
+        constexpr int S0 = 64, S1 = 8;
+        const int n0 = num_tiles / S0 + 1, n1 = num_tiles / S1 + 1;
+        nway_partition_kernel<<<(n0 + 63) / 64, 64, 0, ctx->stream>>>(pa, d_bounds, S0, 0);
+        UKM_LAUNCHED(ctx);
+        nway_partition_kernel<<<(n1 + 63) / 64, 64, 0, ctx->stream>>>(pa, d_bounds, S1, S0);
+        UKM_LAUNCHED(ctx);
+        nway_partition_kernel<<<(num_tiles + 1 + 127) / 128, 128, 0, ctx->stream>>>(pa, d_bounds, 1, S1);
+        UKM_LAUNCHED(ctx);
+    }
+    nway_check_kernel<<<(num_tiles + 127) / 128, 128, 0, ctx->stream>>>(d_bounds, num_tiles, cap, d_info);
+    UKM_LAUNCHED(ctx);
+    UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_info, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *bad = reinterpret_cast<int*>(ctx->h_scratch)[0] != 0;
+    *d_bounds_out = d_bounds;
+    *d_status_out = d_status;
+    *num_tiles_out = num_tiles;
+    return UKM_OK;
+}
 
 bool ukm_nway_enabled() {
     const char* e = getenv("UKM_NWAY");

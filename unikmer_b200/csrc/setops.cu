@@ -1352,7 +1352,8 @@ int run_tree(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags,
                 }
                 bool fell_back = false;
                 size_t n_o = 0;
-                UKM_TRY(ukm_nway_union(ctx, ks, ns, (int)gsz, o.k, &n_o, &fell_back));
+                if (ukm_nunion_enabled()) UKM_TRY(ukm_nunion(ctx, ks, ns, (int)gsz, o.k, &n_o, &fell_back));
+                else UKM_TRY(ukm_nway_union(ctx, ks, ns, (int)gsz, o.k, &n_o, &fell_back));
                 if (fell_back) {
                     // inputs that cannot be tiled (not duplicate-free): the rest of the tree runs two-way passes
                     if (!direct) free_set(tmp, &o);
