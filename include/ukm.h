@@ -72,6 +72,11 @@ typedef enum ukm_fold_mode {
 #define UKM_F_SCALED 64u       /* count -D: keep code <= max_hash (count.go:373) */
 #define UKM_F_VALIDATE 128u    /* set ops: verify every input is sorted + duplicate-free first (one extra read);
                                   without it the header flag is trusted, as the reference does (inter.go:139) */
+#define UKM_F_SHARD 256u       /* inter: the spans are key-range SLICES of files (multi-GPU shards, streamed key ranges), not
+                                  whole files: the reference's whole-file quirks are off -- an empty first span gives an empty
+                                  result instead of UKM_E_PANIC (inter.go:208), an empty later span empties the result instead
+                                  of keeping the current set (inter.go:211-215, B-3) -- so that the concatenated per-slice
+                                  results equal the whole-file result.  The caller applies the quirks once, on the file sizes. */
 
 /* One k-mer stream: what unik.Reader.ReadCodeWithTaxid yields for a file, as arrays.
  * Mirrors []uint64 / []CodeTaxid (kmers.go:24-46) in SoA form. */
@@ -149,6 +154,21 @@ int ukm_inter(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_sp
 int ukm_diff(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_span* out);
 /* common.go:220-283,329-354; threshold as computed at common.go:93-105. */
 int ukm_common(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, uint16_t threshold, ukm_span* out);
+
+/* ---- several operations over the same files, streamed from host memory ---------------- */
+/* The reference runs `unikmer inter`, `diff`, `union` as separate commands, each reading every .unik file again
+ * (inter.go:188-203, diff.go:136-146 + 380-435, union.go:186-208).  Host-resident inputs make PCIe the bound of a
+ * GPU step, so this call runs ANY SUBSET of the three over the same inputs with every input byte uploaded ONCE: the
+ * key space is cut into ranges (all three are key-local), the slices of range c+1 are uploaded while the operations
+ * run on range c and the results of range c-1 are downloaded.  outs[k] receives the result of ops[k]; results are
+ * exactly those of ukm_inter / ukm_diff / ukm_union on the whole files (the whole-file rules -- empty first file,
+ * empty later file -- are applied on the file sizes).  Keys only (flags: 0 or UKM_F_VALIDATE); inputs all HOST /
+ * HOST_PINNED (pinned memory is what lets the copies overlap: ukm_alloc_pinned) or all DEVICE (then nothing is
+ * streamed and the call is the three plain calls).  ukm_inter / ukm_diff / ukm_union take the same streamed path
+ * on their own when every input is in host memory. */
+typedef enum ukm_setop { UKM_OP_INTER = 0, UKM_OP_DIFF = 1, UKM_OP_UNION = 2 } ukm_setop;
+int ukm_setops_stream(ukm_ctx* ctx, const ukm_span* in, int n_in, const int* ops, int n_ops, unsigned flags,
+                      ukm_span* outs);
 
 /* ---- count: count.go:314-322 iterators, 355-437 inner loop, 531-595 sort+emit ------ */
 /* bases = concatenated records (line breaks stripped, as bio/seqio/fastx yields them),

@@ -94,6 +94,8 @@ def lib():
         L.orc_universe.restype = None
         L.orc_member_file.argtypes = [C.c_uint64, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, u64p]
         L.orc_member_file.restype = C.c_size_t
+        L.orc_c3_digest.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, u64p]
+        L.orc_c3_digest.restype = None
         L.orc_random_keys.argtypes = [C.c_uint64, C.c_size_t, C.c_uint64, u64p]
         L.orc_random_keys.restype = None
         L.orc_synth_bases.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, C.c_uint64, u8p]
@@ -300,6 +302,21 @@ def member_file(j0: int, count_: int, N: int, S: int, T: int, f: int) -> np.ndar
     out = np.empty(count_, dtype=np.uint64)
     n = lib().orc_member_file(j0, count_, N, S, T, f, out.ctypes.data)
     return out[:n].copy()
+
+
+def c3_digest(j0: int, count_: int, N: int, S: int, T: int, nf: int) -> dict:
+    """{count, sum, xor} of inter / diff / union over files 0..nf-1 of the C3 generator restricted to the universe
+    indices [j0, j0 + count) -- computed from the generator's membership bits, no set operation involved."""
+    out = np.zeros(9, dtype=np.uint64)
+    lib().orc_c3_digest(j0, count_, N, S, T, nf, out.ctypes.data)
+    o = [int(x) for x in out]
+    return {"inter": tuple(o[0:3]), "diff": tuple(o[3:6]), "union": tuple(o[6:9])}
+
+
+def digest3(keys: np.ndarray) -> tuple:
+    """(count, sum mod 2^64, xor) of a key array."""
+    k = np.asarray(keys, dtype=np.uint64)
+    return (int(len(k)), int(np.add.reduce(k, dtype=np.uint64)) if len(k) else 0, int(np.bitwise_xor.reduce(k)) if len(k) else 0)
 
 
 def random_keys(i0: int, count_: int, S: int) -> np.ndarray:

@@ -816,6 +816,30 @@ size_t orc_member_file(uint64_t j0, size_t count, uint64_t N, uint64_t S, uint64
     return m;
 }
 
+/* Digests of inter / diff / union over the files 0..nf-1 of the C3 generator, for the universe indices [j0, j0+count):
+ * the universe keys U_j are strictly increasing, so the three results are the U_j whose membership byte (bits 0..nf-1 of
+ * sm64(T+j)) is all ones / is exactly bit 0 / is non-zero.  out[9] = {count, sum, xor} of inter, diff, union (sum mod
+ * 2^64).  A size-independent check of FULL results at BASELINE sizes (bench.py, tests): the set operations themselves
+ * are checked against orc_inter / orc_diff / orc_union on windows. */
+void orc_c3_digest(uint64_t j0, uint64_t count, uint64_t N, uint64_t S, uint64_t T, int nf, uint64_t* out) {
+    const uint64_t W = (1ull << 62) / N;
+    const uint64_t all = nf >= 64 ? ~0ull : ((1ull << nf) - 1);
+    uint64_t ci = 0, si = 0, xi = 0, cd = 0, sd = 0, xd = 0, cu = 0, su = 0, xu = 0;
+#pragma omp parallel for reduction(+ : ci, si, cd, sd, cu, su) reduction(^ : xi, xd, xu) schedule(static)
+    for (uint64_t i = 0; i < count; ++i) {
+        const uint64_t j = j0 + i;
+        const uint64_t m = mix64(T + j) & all;
+        if (!m) continue;
+        const uint64_t key = j * W + (mix64(S + j) % W);
+        cu++; su += key; xu ^= key;
+        if (m == all) { ci++; si += key; xi ^= key; }
+        if (m == 1) { cd++; sd += key; xd ^= key; }
+    }
+    out[0] = ci; out[1] = si; out[2] = xi;
+    out[3] = cd; out[4] = sd; out[5] = xd;
+    out[6] = cu; out[7] = su; out[8] = xu;
+}
+
 /* C2 keys: sm64(S+i) >> 2 */
 void orc_random_keys(uint64_t i0, size_t count, uint64_t S, uint64_t* out) {
     for (size_t i = 0; i < count; ++i) out[i] = mix64(S + i0 + i) >> 2;

@@ -86,3 +86,33 @@ def test_splitters_and_ownership():
     assert len(s) == 7 and int(s[0]) == (1 << 62) // 8 and int(s[-1]) == 7 * ((1 << 62) // 8)
     assert len(equal_width_splitters(1)) == 0
     assert [owner_of_file(f, 4) for f in range(8)] == [0, 1, 2, 3, 0, 1, 2, 3]
+
+
+def test_pipelined_exchange_plan_pieces_concatenate_to_the_whole_result():
+    """The pipelined exchange (PeerPullExchange.plan_chunks / exchange_chunks) cuts every rank's key range into K pieces and
+    runs the operations piece by piece with UKM_F_SHARD semantics; the concatenation over (rank, piece) must equal the
+    whole-file result.  Checked here on the CPU with the plan's splitters and the oracle as the per-piece operation
+    (inter: an empty slice empties the piece's result -- the shard rule -- instead of the whole-file quirk B-3)."""
+    import oracle
+    from unikmer_b200.dist import equal_width_splitters, fine_splitters
+    N, n_files = 200_000, 8
+    files = [oracle.member_file(0, N, N, 3, 4, f) for f in range(n_files)]
+    files[5] = files[5][files[5] < (1 << 59)]  # a file that has nothing in most pieces
+    for world, K in ((2, 4), (8, 3), (4, 1)):
+        fine = fine_splitters(equal_width_splitters(world, 62), world, K)
+        assert len(fine) == world * K - 1 and (np.diff(fine.astype(np.float64)) > 0).all()
+        cuts = [np.concatenate([[0], np.searchsorted(f, fine, side="left"), [len(f)]]) for f in files]
+        res = {"inter": [], "diff": [], "union": []}
+        for p in range(world * K):
+            sl = [f[c[p]:c[p + 1]] for f, c in zip(files, cuts)]
+            if all(len(x) for x in sl):
+                res["inter"].append(oracle.inter(sl)[0])
+            sub = [x for x in sl[1:] if len(x)]
+            res["diff"].append(oracle.diff([sl[0]] + sub)[0] if len(sl[0]) and sub else sl[0])
+            res["union"].append(oracle.union(sl)[0])
+        exp_i = files[0]
+        for f in files[1:]:
+            exp_i = exp_i[np.isin(exp_i, f)]
+        assert np.array_equal(np.concatenate(res["inter"]) if res["inter"] else np.zeros(0, np.uint64), exp_i)
+        assert np.array_equal(np.concatenate(res["diff"]), oracle.diff(files)[0])
+        assert np.array_equal(np.concatenate(res["union"]), oracle.union(files)[0])

@@ -1,0 +1,119 @@
+"""Streamed set operations on host-resident inputs (ukm_setops_stream; also the path ukm_inter / ukm_diff / ukm_union take
+on their own when every input is in host memory): key ranges uploaded, computed and downloaded as a pipeline, every input
+byte crossing PCIe once.  Results must equal the whole-file results of the oracle (inter.go:188-286, diff.go:380-435,
+union.go:186-208), including the whole-file rules for empty inputs."""
+import numpy as np
+import pytest
+
+import oracle
+from tests.test_gpu_parity import U64, member_files, rng, same
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from unikmer_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(autouse=True)
+def small_chunks(monkeypatch):
+    monkeypatch.setenv("UKM_STREAM_MIN_MB", "0")   # stream whatever the size
+    monkeypatch.setenv("UKM_STREAM_CHUNK_MB", "1")  # many key ranges on small inputs
+
+
+def check(eng, files, what, ops=("inter", "diff", "union")):
+    got = eng.setops(files, ops)
+    exp = {"inter": oracle.inter, "diff": oracle.diff, "union": oracle.union}
+    for o, g in zip(ops, got):
+        same(g, exp[o](files)[0], f"{what}: {o}")
+
+
+@pytest.mark.parametrize("nf", [2, 3, 8])
+def test_stream_matches_oracle(eng, nf):
+    for N in (5_000, 400_000, 2_000_000):
+        check(eng, member_files(N, nf), f"nf {nf} N {N}")
+
+
+def test_stream_single_ops_take_the_streamed_path(eng):
+    files = member_files(1_500_000, 8)
+    same(eng.inter(files)[0], oracle.inter(files)[0], "inter")
+    same(eng.diff(files)[0], oracle.diff(files)[0], "diff")
+    same(eng.union(files)[0], oracle.union(files)[0], "union")
+
+
+def test_stream_any_subset_and_order_of_operations(eng):
+    files = member_files(600_000, 5)
+    check(eng, files, "union only", ("union",))
+    check(eng, files, "diff, inter", ("diff", "inter"))
+    check(eng, files, "twice", ("inter", "inter", "union"))
+
+
+def test_stream_pinned_host_buffers(eng):
+    import torch
+    files = member_files(1_000_000, 8)
+    pin = [torch.from_numpy(f.view(np.int64)).pin_memory() for f in files]
+    outs = [torch.empty(len(files[0]), dtype=torch.int64).pin_memory(), torch.empty(len(files[0]), dtype=torch.int64).pin_memory(),
+            torch.empty(sum(len(f) for f in files), dtype=torch.int64).pin_memory()]
+    gi, gd, gu = eng.setops(pin, ("inter", "diff", "union"), outs=outs)
+    same(gi.numpy().view(U64), oracle.inter(files)[0], "pinned inter")
+    same(gd.numpy().view(U64), oracle.diff(files)[0], "pinned diff")
+    same(gu.numpy().view(U64), oracle.union(files)[0], "pinned union")
+
+
+def test_stream_distributions_and_empty_files(eng):
+    import unikmer_b200 as ub
+    r = rng(7)
+    base = np.unique(r.integers(0, 2**64, 400_000, dtype=U64))
+    cases = {
+        "extremes": [np.unique(np.concatenate([base[r.random(len(base)) < 0.6], np.array([0, 2**64 - 1], dtype=U64)])) for _ in range(4)],
+        "disjoint ranges": [np.unique(r.integers(q << 50, (q << 50) + 2**30, 30_000 << (q % 3), dtype=U64)) for q in range(5)],
+        "largest is not first": [base[::7].copy(), base.copy(), base[::3].copy()],
+        "clustered": [np.unique(np.concatenate([r.integers(0, 2**63, 20_000, dtype=U64), U64(10**12) + np.arange(q, 300_000, 1 + q, dtype=U64)]))
+                      for q in range(4)],
+        # inter.go:211-215: an empty later file ends the loop and keeps the current set (B-3), on the WHOLE files
+        "empty later file": [base[::2].copy(), base[::3].copy(), np.zeros(0, dtype=U64), base[::5].copy()],
+        "tiny": [np.array([1, 5, 9], dtype=U64), np.array([5], dtype=U64), np.array([5, 9], dtype=U64)],
+    }
+    for name, files in cases.items():
+        got = eng.setops(files, ("inter", "diff", "union"))
+        same(got[0], oracle.inter(files)[0], f"{name}: inter")
+        exp_d = files[0]
+        for f in files[1:]:
+            exp_d = exp_d[~np.isin(exp_d, f)]  # an empty subject is skipped (documented deviation B-5)
+        same(got[1], exp_d, f"{name}: diff")
+        same(got[2], oracle.union(files)[0], f"{name}: union")
+    with pytest.raises(ub.UkmError) as e:  # inter.go:208 panics on an empty first file
+        eng.setops([np.zeros(0, dtype=U64), base], ("inter",))
+    assert e.value.status == ub.E_PANIC
+
+
+def test_stream_capacity_error(eng):
+    import unikmer_b200 as ub
+    files = member_files(300_000, 3)
+    small = np.empty(10, dtype=U64)
+    with pytest.raises(ub.UkmError) as e:
+        eng.setops(files, ("union",), outs=[small])
+    assert e.value.status == ub.E_CAPACITY
+
+
+def test_stale_device_error_is_not_reported_by_the_next_call(eng):
+    """A call that fails after a kernel set the device error word (unsorted input under UKM_F_VALIDATE) must not leave it
+    behind for the next, unrelated call."""
+    import unikmer_b200 as ub
+    bad = np.array([5, 3, 9, 9], dtype=U64)
+    good = member_files(50_000, 2)
+    with pytest.raises(ub.UkmError):
+        eng.union([bad, good[0]], validate=True)
+    same(eng.union(good)[0], oracle.union(good)[0], "call after a failed one")
+
+
+def test_inter_shard_flag_turns_whole_file_quirks_off(eng):
+    base = member_files(100_000, 3)
+    empty = np.zeros(0, dtype=U64)
+    assert len(eng.inter([empty, base[0]], shard=True)[0]) == 0              # no panic: an empty slice, not an empty file
+    assert len(eng.inter([base[0], empty, base[1]], shard=True)[0]) == 0     # plain set semantics, not quirk B-3
+    same(eng.inter([base[0], empty, base[1]])[0], base[0], "B-3 on whole files keeps the current set")

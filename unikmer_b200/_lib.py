@@ -13,7 +13,8 @@ OK, E_ARG, E_CUDA, E_NOMEM, E_CAPACITY, E_NOT_SORTED_UNIQUE, E_ILLEGAL_BASE, E_N
     0, -1, -2, -3, -4, -5, -6, -7, -8, -9)
 HOST, HOST_PINNED, DEVICE = 0, 1, 2
 FOLD_PLAIN, FOLD_UNIQUE, FOLD_REPEATED_FINAL, FOLD_REPEATED_CHUNK = 0, 1, 2, 3
-F_TAXID, F_MIX_TAXID, F_COMPARE_TAXID, F_CANONICAL, F_HASHED, F_CIRCULAR, F_SCALED, F_VALIDATE = 1, 2, 4, 8, 16, 32, 64, 128
+OP_INTER, OP_DIFF, OP_UNION = 0, 1, 2
+F_TAXID, F_MIX_TAXID, F_COMPARE_TAXID, F_CANONICAL, F_HASHED, F_CIRCULAR, F_SCALED, F_VALIDATE, F_SHARD = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 # every symbol include/ukm.h declares (tests check that the library exports all of them)
 SYMBOLS = [
@@ -22,7 +23,7 @@ SYMBOLS = [
     "ukm_launch_count", "ukm_stats_enable", "ukm_stats_reset", "ukm_stats_get",
     "ukm_set_taxonomy", "ukm_lca_batch",
     "ukm_sort_u64", "ukm_sort_pairs", "ukm_sort_codetaxid16",
-    "ukm_fold_sorted", "ukm_merge_sorted", "ukm_union", "ukm_inter", "ukm_diff", "ukm_common",
+    "ukm_fold_sorted", "ukm_merge_sorted", "ukm_union", "ukm_inter", "ukm_diff", "ukm_common", "ukm_setops_stream",
     "ukm_count_seq", "ukm_kmers_seq", "ukm_count_minimizer",
     "ukm_partition_sorted", "ukm_check_sorted_unique",
     "ukm_synth_random_keys", "ukm_synth_member_file", "ukm_synth_bases",
@@ -76,6 +77,7 @@ def load():
         "ukm_merge_sorted": ([vp, i, SP, i, u, SP], i),
         "ukm_union": ([vp, SP, i, u, SP], i), "ukm_inter": ([vp, SP, i, u, SP], i),
         "ukm_diff": ([vp, SP, i, u, SP], i), "ukm_common": ([vp, SP, i, u, C.c_uint16, SP], i),
+        "ukm_setops_stream": ([vp, SP, i, C.POINTER(i), i, u, SP], i),
         "ukm_count_seq": ([vp, vp, vp, sz, i, u, u64, i, SP], i),
         "ukm_kmers_seq": ([vp, vp, vp, sz, i, u, u64, i, SP], i),
         "ukm_count_minimizer": ([vp, vp, vp, sz, i, i, u, u64, i, SP], i),

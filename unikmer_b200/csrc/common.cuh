@@ -53,9 +53,17 @@ struct ukm_ctx {
     std::vector<cudaEvent_t> event_pool;
     // per-context (= per-device) kernel set-up: dynamic shared-memory opt-in done, resident CTAs per SM (-1 = not asked)
     std::map<const void*, int> kcfg;
+    // a call that failed after a kernel wrote the device error word may have left it set: the next call clears it first
+    bool err_stale = false;
+    // streamed operations on host inputs (ukm_setops_stream): copy streams beside the compute stream, created on first use
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_misc = nullptr;
 };
 
 int ukm_fail(ukm_ctx* ctx, int code, const char* fmt, ...);
+// first thing every compute entry point does: make the context's device current and drop a device error word that an
+// earlier, failed call left behind (so a stale NOT_SORTED_UNIQUE / ILLEGAL_BASE is never reported by an unrelated call)
+int ukm_begin_call(ukm_ctx* ctx);
 
 #define UKM_CUDA(ctx, call)                                                                        \
     do {                                                                                           \

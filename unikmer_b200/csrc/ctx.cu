@@ -9,8 +9,22 @@ int ukm_fail(ukm_ctx* ctx, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (ctx) ctx->err = buf;
+    if (ctx) {
+        ctx->err = buf;
+        ctx->err_stale = true;
+    }
     return code;
+}
+
+int ukm_begin_call(ukm_ctx* ctx) {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return ukm_fail(ctx, UKM_E_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    if (ctx->err_stale) {
+        e = cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream);
+        if (e != cudaSuccess) return ukm_fail(ctx, UKM_E_CUDA, "clearing the device error word: %s", cudaGetErrorString(e));
+        ctx->err_stale = false;
+    }
+    return UKM_OK;
 }
 
 static thread_local std::string g_create_err;
@@ -70,6 +84,13 @@ extern "C" void ukm_destroy(ukm_ctx* ctx) {
         cudaEventDestroy(p.b);
     }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    for (int q = 0; q < 2; ++q) {
+        if (ctx->ev_in[q]) cudaEventDestroy(ctx->ev_in[q]);
+        if (ctx->ev_out[q]) cudaEventDestroy(ctx->ev_out[q]);
+    }
+    if (ctx->ev_misc) cudaEventDestroy(ctx->ev_misc);
     cudaFree(ctx->tax.parent);
     cudaFree(ctx->tax.merged);
     cudaFree(ctx->tax.depth);

@@ -185,7 +185,7 @@ extern "C" int ukm_fold_sorted(ukm_ctx* ctx, int mode, const ukm_span* in, unsig
     if (!ctx) return UKM_E_ARG;
     if (!in || !out) return ukm_fail(ctx, UKM_E_ARG, "ukm_fold_sorted: NULL span");
     if (mode < UKM_FOLD_PLAIN || mode > UKM_FOLD_REPEATED_CHUNK) return ukm_fail(ctx, UKM_E_ARG, "ukm_fold_sorted: bad mode");
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     const bool tax = (flags & UKM_F_TAXID) != 0;
     if (tax && mode != UKM_FOLD_PLAIN && !ctx->tax.parent)
         return ukm_fail(ctx, UKM_E_NO_TAXONOMY, "ukm_fold_sorted: taxids requested but no taxonomy loaded");
@@ -245,7 +245,7 @@ extern "C" int ukm_check_sorted_unique(ukm_ctx* ctx, const ukm_span* in) {
     if (!ctx) return UKM_E_ARG;
     if (!in) return ukm_fail(ctx, UKM_E_ARG, "ukm_check_sorted_unique: NULL span");
     if (in->n < 2) return UKM_OK;
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     ukm_tmp tmp(ctx);
     ukm_dspan d;
     UKM_TRY(ukm_stage_in(ctx, tmp, in, false, &d));
@@ -256,7 +256,7 @@ extern "C" int ukm_check_sorted_unique(ukm_ctx* ctx, const ukm_span* in) {
 extern "C" int ukm_partition_sorted(ukm_ctx* ctx, const ukm_span* in, const uint64_t* splitters, int n_split, uint64_t* offsets) {
     if (!ctx) return UKM_E_ARG;
     if (!in || !offsets || n_split < 0 || (n_split && !splitters)) return ukm_fail(ctx, UKM_E_ARG, "ukm_partition_sorted: bad argument");
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     offsets[0] = 0;
     offsets[n_split + 1] = in->n;
     if (n_split == 0) return UKM_OK;

@@ -583,7 +583,7 @@ extern "C" int ukm_kmers_seq(ukm_ctx* ctx, const uint8_t* bases, const uint64_t*
                              uint64_t max_hash, int where, ukm_span* out) {
     if (!ctx) return UKM_E_ARG;
     if (!out) return ukm_fail(ctx, UKM_E_ARG, "ukm_kmers_seq: out == NULL");
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     ukm_tmp tmp(ctx);
     Prepared P;
     UKM_TRY(prepare(ctx, tmp, bases, rec_off, n_rec, k, flags, where, &P, "ukm_kmers_seq"));
@@ -613,7 +613,7 @@ extern "C" int ukm_count_seq(ukm_ctx* ctx, const uint8_t* bases, const uint64_t*
                              uint64_t max_hash, int where, ukm_span* out) {
     if (!ctx) return UKM_E_ARG;
     if (!out) return ukm_fail(ctx, UKM_E_ARG, "ukm_count_seq: out == NULL");
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     ukm_tmp tmp(ctx);
     Prepared P;
     UKM_TRY(prepare(ctx, tmp, bases, rec_off, n_rec, k, flags, where, &P, "ukm_count_seq"));
@@ -719,7 +719,7 @@ extern "C" int ukm_count_minimizer(ukm_ctx* ctx, const uint8_t* bases, const uin
     if (!ctx) return UKM_E_ARG;
     if (!out) return ukm_fail(ctx, UKM_E_ARG, "ukm_count_minimizer: out == NULL");
     if (w < 1) return ukm_fail(ctx, UKM_E_ARG, "ukm_count_minimizer: w=%d", w);
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     flags |= UKM_F_HASHED;  // count.go:105-109: -W switches -H on
     ukm_tmp tmp(ctx);
     Prepared P;

@@ -419,7 +419,7 @@ static int sort_common(ukm_ctx* ctx, uint64_t* keys, uint32_t* taxids, size_t n,
     if (!ctx) return UKM_E_ARG;
     if (n && !keys) return ukm_fail(ctx, UKM_E_ARG, "%s: keys == NULL", what);
     if (n < 2) return UKM_OK;
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     if (where == UKM_DEVICE) {
         UKM_TRY(ukm_dev_sort(ctx, keys, taxids, n, key_bits));
         return ukm_check_dev_error(ctx, what);
@@ -452,7 +452,7 @@ extern "C" int ukm_sort_codetaxid16(ukm_ctx* ctx, void* aos16, size_t n, int key
     if (!ctx) return UKM_E_ARG;
     if (n && !aos16) return ukm_fail(ctx, UKM_E_ARG, "ukm_sort_codetaxid16: NULL");
     if (n < 2) return UKM_OK;
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     ukm_tmp tmp(ctx);
     ulonglong2* d_aos = nullptr;
     uint64_t* dk = nullptr;

@@ -1151,7 +1151,7 @@ int check_args(ukm_ctx* ctx, const ukm_span* in, int n_in, ukm_span* out, const 
     if (!in || n_in < 1 || !out) return ukm_fail(ctx, UKM_E_ARG, "%s: need at least one input span and an output span", what);
     for (int i = 0; i < n_in; ++i)
         if (in[i].n > ((size_t)1 << 40)) return ukm_fail(ctx, UKM_E_ARG, "%s: input %d too large", what, i);
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     return UKM_OK;
 }
 
@@ -1195,8 +1195,17 @@ int run_chain(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags
     int i = 1;
     while (i < n_in) {
         if (op == OP_INTER) {
-            if (cur.n == 0 && cur_is_input) return ukm_fail(ctx, UKM_E_PANIC, "%s: first input is empty (inter.go:208 panics)", what);
-            if (in[i].n == 0) break;  // inter.go:211-215: flagBreak keeps the current set (quirk B-3)
+            // Whole-file quirks of the reference: an empty first file panics (inter.go:208), an empty later file ends the
+            // loop and KEEPS the current set (inter.go:211-215, quirk B-3).  A key-range SLICE of a file (UKM_F_SHARD:
+            // multi-GPU shards, streamed key ranges) can be empty when the file is not; there the plain set semantics
+            // apply -- an empty input makes the intersection of that range empty -- so that the concatenation of the
+            // slices' results equals the whole-file result.
+            if (flags & UKM_F_SHARD) {
+                if (in[i].n == 0) cur.n = 0;
+            } else {
+                if (cur.n == 0 && cur_is_input) return ukm_fail(ctx, UKM_E_PANIC, "%s: first input is empty (inter.go:208 panics)", what);
+                if (in[i].n == 0) break;  // inter.go:211-215: flagBreak keeps the current set (quirk B-3)
+            }
         }
         if (op == OP_DIFF && in[i].n == 0) { ++i; continue; }
         if (cur.n == 0) break;
@@ -1392,23 +1401,213 @@ int run_tree(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags,
     return ukm_deliver(ctx, r.k, tax ? r.t : nullptr, r.n, out);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// streamed operations on HOST inputs: every input byte crosses PCIe once, uploads / kernels / downloads overlap
+// ---------------------------------------------------------------------------------------------------
+// All set operations are key-local, so a step over host-resident files can run as a stream of key ranges: the slices
+// of range c + 1 are uploaded (copy-in stream) while the requested operations run on range c (context stream) and the
+// results of range c - 1 travel back (copy-out stream).  Ranges are quantiles of the largest input; the slices of a
+// range are found by binary search on the host arrays.  Device memory: two sets of slice buffers + two sets of result
+// buffers, sized for the largest range.
+constexpr size_t STREAM_CHUNK_BYTES = (size_t)2 << 30;  // input bytes per key range (UKM_STREAM_CHUNK_MB overrides)
+
+struct StreamPlan {
+    int K = 1;                               // key ranges
+    std::vector<std::vector<size_t>> off;    // off[f][c] .. off[f][c+1] = slice of file f in range c
+};
+
+void stream_plan(const ukm_span* in, int n_in, size_t chunk_bytes, StreamPlan* pl) {
+    size_t total = 0, big = 0;
+    int bigf = 0;
+    for (int f = 0; f < n_in; ++f) {
+        total += in[f].n;
+        if (in[f].n > big) { big = in[f].n; bigf = f; }
+    }
+    size_t K = (total * 8 + chunk_bytes - 1) / chunk_bytes;
+    if (K < 1) K = 1;
+    if (K > big && big > 0) K = big;
+    if (K > 4096) K = 4096;
+    pl->K = (int)K;
+    pl->off.assign(n_in, std::vector<size_t>(K + 1, 0));
+    for (int f = 0; f < n_in; ++f) pl->off[f][K] = in[f].n;
+    for (size_t c = 1; c < K; ++c) {
+        const uint64_t cut = in[bigf].keys[big * c / K];  // range c starts at this key
+        for (int f = 0; f < n_in; ++f) {
+            const uint64_t* b = in[f].keys;
+            size_t lo = pl->off[f][c - 1], hi = in[f].n;  // lower_bound(cut), monotone in c
+            while (lo < hi) {
+                const size_t mid = lo + ((hi - lo) >> 1);
+                if (b[mid] < cut) lo = mid + 1;
+                else hi = mid;
+            }
+            pl->off[f][c] = lo;
+        }
+    }
+}
+
+int stream_run(ukm_ctx* ctx, const ukm_span* in, int n_in, const int* ops, int n_ops, unsigned flags, ukm_span* outs) {
+    size_t chunk_bytes = STREAM_CHUNK_BYTES;
+    if (const char* e = getenv("UKM_STREAM_CHUNK_MB")) {
+        const long v = atol(e);
+        if (v > 0) chunk_bytes = (size_t)v << 20;
+    }
+    StreamPlan pl;
+    stream_plan(in, n_in, chunk_bytes, &pl);
+    const int K = pl.K;
+    // the reference's whole-file rules, applied once on the file sizes (the per-range calls run with UKM_F_SHARD)
+    int n_inter = n_in;  // inter.go:211-215: the loop ends at the first empty later file and keeps the current set (B-3)
+    for (int f = 1; f < n_in; ++f)
+        if (in[f].n == 0) { n_inter = f; break; }
+    for (int k = 0; k < n_ops; ++k)
+        if (ops[k] == UKM_OP_INTER && in[0].n == 0)
+            return ukm_fail(ctx, UKM_E_PANIC, "ukm_setops_stream: first input is empty (inter.go:208 panics)");
+    // buffers: the largest range decides
+    size_t max_in = 0, max_f0 = 0;
+    for (int c = 0; c < K; ++c) {
+        size_t sum = 0;
+        for (int f = 0; f < n_in; ++f) sum += pl.off[f][c + 1] - pl.off[f][c] + 2;  // + 2: 16-byte aligned slice starts
+        if (sum > max_in) max_in = sum;
+        const size_t f0 = pl.off[0][c + 1] - pl.off[0][c];
+        if (f0 > max_f0) max_f0 = f0;
+    }
+    if (!ctx->copy_in) {
+        UKM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        UKM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        for (int q = 0; q < 2; ++q) {
+            UKM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[q], cudaEventDisableTiming));
+            UKM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[q], cudaEventDisableTiming));
+        }
+        UKM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_misc, cudaEventDisableTiming));
+    }
+    ukm_tmp tmp(ctx);
+    uint64_t* d_in[2] = {nullptr, nullptr};
+    std::vector<uint64_t*> d_out[2];
+    std::vector<size_t> cap_out(n_ops);
+    for (int k = 0; k < n_ops; ++k) cap_out[k] = (ops[k] == UKM_OP_UNION ? max_in : max_f0) + 2;
+    for (int q = 0; q < 2; ++q) {
+        UKM_TRY(tmp.alloc(&d_in[q], max_in + 2));
+        d_out[q].resize(n_ops);
+        for (int k = 0; k < n_ops; ++k) UKM_TRY(tmp.alloc(&d_out[q][k], cap_out[k]));
+    }
+    // the allocations are ordered on the context stream: the copy streams start after them
+    UKM_CUDA(ctx, cudaEventRecord(ctx->ev_misc, ctx->stream));
+    UKM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_misc, 0));
+    UKM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_misc, 0));
+    std::vector<ukm_span> dsp(n_in);
+    std::vector<size_t> written(n_ops, 0);
+    auto upload = [&](int c) -> int {
+        const int q = c & 1;
+        size_t pos = 0;
+        for (int f = 0; f < n_in; ++f) {
+            const size_t lo = pl.off[f][c], n = pl.off[f][c + 1] - lo;
+            if (n) UKM_CUDA(ctx, cudaMemcpyAsync(d_in[q] + pos, in[f].keys + lo, n * 8, cudaMemcpyHostToDevice, ctx->copy_in));
+            pos += (n + 1) & ~(size_t)1;
+        }
+        UKM_CUDA(ctx, cudaEventRecord(ctx->ev_in[q], ctx->copy_in));
+        return UKM_OK;
+    };
+    int status = UKM_OK;
+    UKM_TRY(upload(0));
+    for (int c = 0; c < K && status == UKM_OK; ++c) {
+        const int q = c & 1;
+        // range c + 1 goes up while range c is computed (its buffer set was last read by range c - 1, which is complete:
+        // every operation below ends with a synchronisation of the context stream)
+        if (c + 1 < K) UKM_TRY(upload(c + 1));
+        UKM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[q], 0));
+        if (c >= 2) UKM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[q], 0));  // result set q: its download has left
+        size_t pos = 0;
+        for (int f = 0; f < n_in; ++f) {
+            const size_t n = pl.off[f][c + 1] - pl.off[f][c];
+            dsp[f] = in[f];
+            dsp[f].keys = d_in[q] + pos;
+            dsp[f].taxids = nullptr;
+            dsp[f].n = dsp[f].cap = n;
+            dsp[f].where = UKM_DEVICE;
+            pos += (n + 1) & ~(size_t)1;
+        }
+        size_t n_res[8] = {0};
+        for (int k = 0; k < n_ops && status == UKM_OK; ++k) {
+            ukm_span o;
+            memset(&o, 0, sizeof o);
+            o.keys = d_out[q][k];
+            o.cap = cap_out[k];
+            o.where = UKM_DEVICE;
+            if (ops[k] == UKM_OP_INTER) status = run_chain(ctx, OP_INTER, dsp.data(), n_inter, (flags & UKM_F_VALIDATE) | UKM_F_SHARD, &o, "ukm_setops_stream(inter)");
+            else if (ops[k] == UKM_OP_DIFF) status = run_chain(ctx, OP_DIFF, dsp.data(), n_in, flags & UKM_F_VALIDATE, &o, "ukm_setops_stream(diff)");
+            else status = run_tree(ctx, OP_UNION, dsp.data(), n_in, flags & UKM_F_VALIDATE, false, 0, UKM_FOLD_PLAIN, &o, "ukm_setops_stream(union)");
+            n_res[k] = o.n;
+        }
+        if (status != UKM_OK) break;
+        // results of range c travel back while range c + 1 is computed
+        UKM_CUDA(ctx, cudaEventRecord(ctx->ev_misc, ctx->stream));
+        UKM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_misc, 0));
+        for (int k = 0; k < n_ops; ++k) {
+            if (written[k] + n_res[k] > outs[k].cap) {
+                outs[k].n = written[k] + n_res[k];
+                status = ukm_fail(ctx, UKM_E_CAPACITY, "ukm_setops_stream: output %d needs more than %zu elements", k, outs[k].cap);
+                break;
+            }
+            if (n_res[k])
+                UKM_CUDA(ctx, cudaMemcpyAsync(outs[k].keys + written[k], d_out[q][k], n_res[k] * 8,
+                                              outs[k].where == UKM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->copy_out));
+            written[k] += n_res[k];
+        }
+        UKM_CUDA(ctx, cudaEventRecord(ctx->ev_out[q], ctx->copy_out));
+    }
+    // drain both copy streams before the buffers go back to the pool (also on errors)
+    cudaStreamSynchronize(ctx->copy_in);
+    cudaStreamSynchronize(ctx->copy_out);
+    if (status != UKM_OK) return status;
+    for (int k = 0; k < n_ops; ++k) outs[k].n = written[k];
+    return UKM_OK;
+}
+
+// can this call take the streamed path: keys only, every input in host memory, sorted subjects
+bool stream_eligible(const ukm_span* in, int n_in, unsigned flags) {
+    if (flags & (UKM_F_TAXID | UKM_F_MIX_TAXID | UKM_F_COMPARE_TAXID)) return false;
+    size_t total = 0;
+    for (int f = 0; f < n_in; ++f) {
+        if (in[f].where == UKM_DEVICE || !in[f].sorted) return false;
+        if (in[f].n && !in[f].keys) return false;
+        total += in[f].n;
+    }
+    const char* e = getenv("UKM_STREAM");
+    if (e && e[0] == '0') return false;
+    size_t min_bytes = (size_t)64 << 20;  // small inputs: one upload is as fast and saves the bookkeeping
+    if (const char* m = getenv("UKM_STREAM_MIN_MB")) min_bytes = (size_t)atol(m) << 20;  // tests
+    return total * 8 >= min_bytes;
+}
+
 }  // namespace
 
 extern "C" int ukm_inter(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_span* out) {
     UKM_TRY(check_args(ctx, in, n_in, out, "ukm_inter"));
     UKM_TRY(need_tax(ctx, flags & ~UKM_F_MIX_TAXID, "ukm_inter"));
+    if (!(flags & UKM_F_SHARD) && stream_eligible(in, n_in, flags)) {
+        const int op = UKM_OP_INTER;
+        return stream_run(ctx, in, n_in, &op, 1, flags, out);
+    }
     return run_chain(ctx, OP_INTER, in, n_in, flags, out, "ukm_inter");
 }
 
 extern "C" int ukm_diff(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_span* out) {
     UKM_TRY(check_args(ctx, in, n_in, out, "ukm_diff"));
     if ((flags & UKM_F_COMPARE_TAXID) && (flags & UKM_F_TAXID)) UKM_TRY(need_tax(ctx, flags, "ukm_diff"));
+    if (stream_eligible(in, n_in, flags)) {
+        const int op = UKM_OP_DIFF;
+        return stream_run(ctx, in, n_in, &op, 1, flags, out);
+    }
     return run_chain(ctx, OP_DIFF, in, n_in, flags & ~UKM_F_MIX_TAXID, out, "ukm_diff");
 }
 
 extern "C" int ukm_union(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_span* out) {
     UKM_TRY(check_args(ctx, in, n_in, out, "ukm_union"));
     UKM_TRY(need_tax(ctx, flags & UKM_F_TAXID, "ukm_union"));
+    if (stream_eligible(in, n_in, flags)) {
+        const int op = UKM_OP_UNION;
+        return stream_run(ctx, in, n_in, &op, 1, flags, out);
+    }
     return run_tree(ctx, OP_UNION, in, n_in, flags & (UKM_F_TAXID | UKM_F_VALIDATE), false, 0, UKM_FOLD_PLAIN, out, "ukm_union");
 }
 
@@ -1423,4 +1622,35 @@ extern "C" int ukm_merge_sorted(ukm_ctx* ctx, int mode, const ukm_span* in, int 
     if (mode < UKM_FOLD_PLAIN || mode > UKM_FOLD_REPEATED_CHUNK) return ukm_fail(ctx, UKM_E_ARG, "ukm_merge_sorted: bad mode");
     if (mode != UKM_FOLD_PLAIN) UKM_TRY(need_tax(ctx, flags & UKM_F_TAXID, "ukm_merge_sorted"));
     return run_tree(ctx, OP_MERGE, in, n_in, flags & UKM_F_TAXID, false, 0, mode, out, "ukm_merge_sorted");
+}
+
+extern "C" int ukm_setops_stream(ukm_ctx* ctx, const ukm_span* in, int n_in, const int* ops, int n_ops, unsigned flags,
+                                 ukm_span* outs) {
+    if (!ctx) return UKM_E_ARG;
+    if (!ops || n_ops < 1 || n_ops > 8 || !outs) return ukm_fail(ctx, UKM_E_ARG, "ukm_setops_stream: 1..8 operations and their output spans");
+    UKM_TRY(check_args(ctx, in, n_in, outs, "ukm_setops_stream"));
+    for (int k = 0; k < n_ops; ++k) {
+        if (ops[k] != UKM_OP_INTER && ops[k] != UKM_OP_DIFF && ops[k] != UKM_OP_UNION)
+            return ukm_fail(ctx, UKM_E_ARG, "ukm_setops_stream: unknown operation %d", ops[k]);
+        if (outs[k].cap && !outs[k].keys) return ukm_fail(ctx, UKM_E_ARG, "ukm_setops_stream: output %d has keys == NULL", k);
+    }
+    if (flags & (UKM_F_TAXID | UKM_F_MIX_TAXID | UKM_F_COMPARE_TAXID))
+        return ukm_fail(ctx, UKM_E_ARG, "ukm_setops_stream: keys only (taxid-carrying operations go through ukm_inter / ukm_diff / ukm_union)");
+    bool host = true, dev = true, sorted = true;
+    for (int f = 0; f < n_in; ++f) {
+        host &= in[f].where != UKM_DEVICE;
+        dev &= in[f].where == UKM_DEVICE;
+        sorted &= in[f].sorted != 0;
+    }
+    if (!host && !dev) return ukm_fail(ctx, UKM_E_ARG, "ukm_setops_stream: all inputs must live in the same memory space");
+    if (host && sorted) return stream_run(ctx, in, n_in, ops, n_ops, flags, outs);
+    // device-resident inputs (nothing to stream) or an unsorted diff subject: the plain calls, one after the other
+    for (int k = 0; k < n_ops; ++k) {
+        int r;
+        if (ops[k] == UKM_OP_INTER) r = run_chain(ctx, OP_INTER, in, n_in, flags & UKM_F_VALIDATE, &outs[k], "ukm_setops_stream(inter)");
+        else if (ops[k] == UKM_OP_DIFF) r = run_chain(ctx, OP_DIFF, in, n_in, flags & UKM_F_VALIDATE, &outs[k], "ukm_setops_stream(diff)");
+        else r = run_tree(ctx, OP_UNION, in, n_in, flags & UKM_F_VALIDATE, false, 0, UKM_FOLD_PLAIN, &outs[k], "ukm_setops_stream(union)");
+        UKM_TRY(r);
+    }
+    return UKM_OK;
 }

@@ -37,7 +37,7 @@ extern "C" int ukm_synth_random_keys(ukm_ctx* ctx, uint64_t i0, size_t count, ui
     if (!ctx) return UKM_E_ARG;
     if (count && !d_out) return ukm_fail(ctx, UKM_E_ARG, "ukm_synth_random_keys: NULL");
     if (!count) return UKM_OK;
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     random_keys_kernel<<<ukm_grid_for(count, 256 * 8, ctx->sm_count), 256, 0, ctx->stream>>>(i0, count, seed, d_out);
     UKM_LAUNCHED(ctx);
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -48,7 +48,7 @@ extern "C" int ukm_synth_member_file(ukm_ctx* ctx, uint64_t j0, size_t count, ui
                                      uint64_t* d_out, size_t* n_out) {
     if (!ctx) return UKM_E_ARG;
     if (!n_out || (count && !d_out) || N == 0 || f > 63) return ukm_fail(ctx, UKM_E_ARG, "ukm_synth_member_file: bad argument");
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     MemberGen g{j0, (1ull << 62) / N, S, T, f};
     UKM_TRY(ukm_dev_select(ctx, g, count, d_out, n_out, "synth_member", 0.0));
     return ukm_check_dev_error(ctx, "ukm_synth_member_file");
@@ -58,7 +58,7 @@ extern "C" int ukm_synth_bases(ukm_ctx* ctx, uint64_t r, uint64_t i0, size_t cou
     if (!ctx) return UKM_E_ARG;
     if (count && !d_out) return ukm_fail(ctx, UKM_E_ARG, "ukm_synth_bases: NULL");
     if (!count) return UKM_OK;
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     synth_bases_kernel<<<ukm_grid_for(count, 256 * 8, ctx->sm_count), 256, 0, ctx->stream>>>(r, i0, count, S, d_out);
     UKM_LAUNCHED(ctx);
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

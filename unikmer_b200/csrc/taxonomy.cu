@@ -19,7 +19,7 @@ extern "C" int ukm_set_taxonomy(ukm_ctx* ctx, const uint32_t* parent, size_t n, 
     if (!ctx) return UKM_E_ARG;
     if (!parent || n == 0) return ukm_fail(ctx, UKM_E_ARG, "ukm_set_taxonomy: empty parent table");
     if (n_merged && (!merged_from || !merged_to)) return ukm_fail(ctx, UKM_E_ARG, "ukm_set_taxonomy: merged arrays NULL");
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     size_t nn = n;
     for (size_t i = 0; i < n_merged; ++i)
         if ((size_t)merged_from[i] + 1 > nn) nn = (size_t)merged_from[i] + 1;
@@ -74,7 +74,7 @@ extern "C" int ukm_lca_batch(ukm_ctx* ctx, const uint32_t* a, const uint32_t* b,
     if (!ctx) return UKM_E_ARG;
     if (n && (!a || !b || !out)) return ukm_fail(ctx, UKM_E_ARG, "ukm_lca_batch: NULL");
     if (n == 0) return UKM_OK;
-    UKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    UKM_TRY(ukm_begin_call(ctx));
     ukm_tmp tmp(ctx);
     const uint32_t *da = a, *db = b;
     uint32_t* dout = out;

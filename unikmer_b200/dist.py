@@ -28,6 +28,17 @@ def equal_width_splitters(world: int, key_bits: int = 62) -> np.ndarray:
     return np.array([((i << key_bits) // world) for i in range(1, world)], dtype=np.uint64)
 
 
+def fine_splitters(splitters: np.ndarray, world: int, chunks: int, key_hi: int = 1 << 62) -> np.ndarray:
+    """Cut every rank's key range [s[r-1], s[r]) into `chunks` equal-width pieces: G*K - 1 splitters, fine range r*K + c is
+    piece c of rank r (the rank boundaries themselves are among them)."""
+    edges = [0] + [int(x) for x in splitters] + [int(key_hi)]
+    fine = []
+    for r in range(world):
+        lo, hi = edges[r], edges[r + 1]
+        fine += [lo + (hi - lo) * c // chunks for c in range(chunks)]
+    return np.array(fine[1:], dtype=np.uint64)
+
+
 def owner_of_file(f: int, world: int) -> int:
     """Initial placement: file f lives on rank f mod G (files arrive from different readers)."""
     return f % world
@@ -196,3 +207,66 @@ class PeerPullExchange:
         for f in files:
             if events[f] is not None:
                 cur.wait_event(events[f])
+
+    # ---- pipelined form: the rank's key range in `chunks` pieces, piece c + 1 pulled while piece c is computed ----
+    def plan_chunks(self, splitters: np.ndarray, chunks: int, key_hi: int = 1 << 62):
+        """Cut every rank's key range [s[r-1], s[r]) into `chunks` equal-width pieces and find, ONCE, where every file
+        is cut (the owners binary-search their files, one all-reduce shares the positions).  The plan stays valid as
+        long as the resident files do not change; exchange_chunks() reuses it every step -- no per-step collective,
+        no host round trip for the bounds."""
+        G, K = self.world, int(chunks)
+        fine = fine_splitters(splitters, G, K, key_hi)
+        bounds = torch.zeros(self.n_files, G * K + 1, dtype=torch.int64)
+        for f, t in self.local.items():
+            bounds[f] = torch.from_numpy(np.asarray(self.backend.partition_sorted(t, fine), dtype=np.int64))
+        b = bounds.to(self.device)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group)
+        self.chunk_bounds = b.cpu()
+        self.chunks = K
+        self.chunk_bufs: Dict[tuple, torch.Tensor] = {}
+        self.chunk_done = [None, None]  # event after the compute that last read buffer set q
+
+    def exchange_chunks(self):
+        """Generator over the pieces of this rank's key range: yields (slices, events) like exchange_async.  The pulls
+        of piece c + 1 are queued on the copy engines before piece c is handed out, into the other buffer set; a set is
+        overwritten only after the compute that read it (everything the consumer queued before asking for the next
+        piece) has finished."""
+        G, me, K = self.world, self.rank, self.chunks
+        cur = torch.cuda.current_stream(self.device)
+
+        def issue(c):
+            q = c & 1
+            slices: List[torch.Tensor] = [None] * self.n_files  # type: ignore
+            events: List[torch.cuda.Event] = [None] * self.n_files  # type: ignore
+            i = 0
+            for f in range(self.n_files):
+                lo, hi = int(self.chunk_bounds[f, me * K + c]), int(self.chunk_bounds[f, me * K + c + 1])
+                if f in self.local:
+                    slices[f] = self.local[f][lo:hi]
+                    continue
+                n = hi - lo
+                buf = self.chunk_bufs.get((f, q))
+                if buf is None or buf.shape[0] < n:
+                    buf = torch.empty(int(n * 1.05) + 16, dtype=self.peer[f].dtype, device=self.device)
+                    self.chunk_bufs[(f, q)] = buf
+                s = self.streams[i % len(self.streams)]
+                i += 1
+                if self.chunk_done[q] is not None:
+                    s.wait_event(self.chunk_done[q])
+                with torch.cuda.stream(s):
+                    buf[:n].copy_(self.peer[f][lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(s)
+                slices[f] = buf[:n]
+                events[f] = ev
+            return slices, events
+
+        nxt = issue(0)
+        for c in range(K):
+            now = nxt
+            if c + 1 < K:
+                nxt = issue(c + 1)
+            yield now
+            done = torch.cuda.Event()
+            done.record(cur)
+            self.chunk_done[c & 1] = done

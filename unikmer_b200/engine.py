@@ -256,10 +256,13 @@ class Engine:
         self._chk(self.lib.ukm_union(self.ctx, arr, len(arr), (L.F_TAXID if has_taxid else 0) | (L.F_VALIDATE if validate else 0), C.byref(out)))
         return self._trim(out, k, t)
 
-    def inter(self, sets: Sequence, has_taxid: bool = False, mix_taxid: bool = False, out=None, validate: bool = False):
-        """`unikmer inter [--mix-taxid]` (inter.go:188-286), iterated in file order."""
+    def inter(self, sets: Sequence, has_taxid: bool = False, mix_taxid: bool = False, out=None, validate: bool = False,
+              shard: bool = False):
+        """`unikmer inter [--mix-taxid]` (inter.go:188-286), iterated in file order.  shard=True: the sets are key-range
+        slices of files (UKM_F_SHARD): plain set semantics for empty slices instead of the whole-file quirks."""
         arr, keep, dev = self._spans(sets)
-        flags = (L.F_TAXID if has_taxid else 0) | (L.F_MIX_TAXID if mix_taxid else 0) | (L.F_VALIDATE if validate else 0)
+        flags = ((L.F_TAXID if has_taxid else 0) | (L.F_MIX_TAXID if mix_taxid else 0) | (L.F_VALIDATE if validate else 0) |
+                 (L.F_SHARD if shard else 0))
         out, k, t = self._span_out(int(arr[0].n), has_taxid or mix_taxid, dev, out)
         self._chk(self.lib.ukm_inter(self.ctx, arr, len(arr), flags, C.byref(out)))
         return self._trim(out, k, t)
@@ -271,6 +274,24 @@ class Engine:
         out, k, t = self._span_out(int(arr[0].n), has_taxid, dev, out)
         self._chk(self.lib.ukm_diff(self.ctx, arr, len(arr), flags, C.byref(out)))
         return self._trim(out, k, t)
+
+    def setops(self, sets: Sequence, ops: Sequence[str] = ("inter", "diff", "union"), outs=None, validate: bool = False):
+        """Several of `inter` / `diff` / `union` over the same k-mer sets in ONE call (ukm_setops_stream): with host-resident
+        sets every input byte crosses PCIe once and uploads, kernels and downloads overlap.  `outs`: one caller-provided
+        key buffer per operation (pinned host tensors for full overlap), or None.  Returns one key array per operation."""
+        arr, keep, dev = self._spans(sets)
+        code = {"inter": L.OP_INTER, "diff": L.OP_DIFF, "union": L.OP_UNION}
+        opc = (C.c_int * len(ops))(*[code[o] for o in ops])
+        total = sum(int(a.n) for a in arr)
+        spans = (L.Span * len(ops))()
+        bufs = []
+        for k, o in enumerate(ops):
+            cap = total if o == "union" else int(arr[0].n)
+            sp, kb, _ = self._span_out(cap, False, dev, None if outs is None else outs[k])
+            spans[k] = sp
+            bufs.append(kb)
+        self._chk(self.lib.ukm_setops_stream(self.ctx, arr, len(arr), opc, len(ops), L.F_VALIDATE if validate else 0, spans))
+        return [b[:int(spans[k].n)] for k, b in enumerate(bufs)]
 
     def common(self, sets: Sequence, threshold: int, has_taxid: bool = False, validate: bool = False):
         """`unikmer common -n threshold` (common.go:220-283, 329-354)."""
