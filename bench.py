@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--exchange-chunks", type=int, default=4, help="N>1: pieces of a rank's key range; piece c+1 is pulled over NVLink while piece c is computed")
+    ap.add_argument("--exchange-chunks", type=int, default=1, help="N>1: pieces of a rank's key range; piece c+1 is pulled over NVLink while piece c is computed")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N>1: NVLink peer pulls (copy engines, overlapped) or one NCCL all-to-all-v")
     args = ap.parse_args()
     args.universe, args.ref_universe, args.cpu_universe = int(args.universe), int(args.ref_universe), int(args.cpu_universe)
@@ -422,6 +422,9 @@ def main():
                         "byte crosses PCIe once per step")
             else:
                 ho = []  # pinned host buffers for the rank's results, sized on the first (warm-up) call
+                if pex is not None:
+                    pex.prefetch_next_step = False  # an end-to-end step pulls nothing before its own upload has finished
+                    pex.chunk_prefetched = None
 
                 def e2e_step():
                     # every rank uploads the files it owns into its resident buffers, then the pipelined NVLink exchange +
@@ -491,8 +494,9 @@ def main():
                                    f"(universe {U:.0e}, {total_in} k-mers in); each op reads all inputs",
                        "inputs": "device-resident, 32 GB >> 126 MB L2 (no L2 flush needed)" if U >= 10**8 else "device-resident",
                        "parallelism": ("1 GPU" if world == 1 else f"key-range shards x{world}, " +
-                                       (f"NVLink peer pulls on the copy engines (CUDA IPC) in {args.exchange_chunks} pieces per rank: piece c+1 is pulled while "
-                                        "the single-pass N-way kernels run on piece c; the exchange plan is made once"
+                                       (f"NVLink peer pulls on the copy engines (CUDA IPC), {args.exchange_chunks} piece(s) per rank and step, double-buffered: "
+                                        "the next piece (the next step's first piece after the last one) is pulled while the single-pass N-way "
+                                        "kernels run on the current one; the exchange plan is made once"
                                         if pex is not None else "one NCCL all-to-all-v per step")),
                        "kmers_per_step": 3 * total_in},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

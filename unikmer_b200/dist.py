@@ -225,6 +225,9 @@ class PeerPullExchange:
         self.chunks = K
         self.chunk_bufs: Dict[tuple, torch.Tensor] = {}
         self.chunk_done = [None, None]  # event after the compute that last read buffer set q
+        self.chunk_prefetched = None
+        self.prefetch_next_step = True
+        self.chunk_seq = 0
 
     def exchange_chunks(self):
         """Generator over the pieces of this rank's key range: yields (slices, events) like exchange_async.  The pulls
@@ -235,7 +238,8 @@ class PeerPullExchange:
         cur = torch.cuda.current_stream(self.device)
 
         def issue(c):
-            q = c & 1
+            q = self.chunk_seq & 1  # buffer sets alternate piece after piece, across steps too
+            self.chunk_seq += 1
             slices: List[torch.Tensor] = [None] * self.n_files  # type: ignore
             events: List[torch.cuda.Event] = [None] * self.n_files  # type: ignore
             i = 0
@@ -259,14 +263,20 @@ class PeerPullExchange:
                     ev.record(s)
                 slices[f] = buf[:n]
                 events[f] = ev
-            return slices, events
+            return slices, events, q
 
-        nxt = issue(0)
+        # piece 0 of this step was queued at the end of the step before (a stream of steps over resident files: the pull of
+        # the next step's first piece overlaps this step's last piece, so only the very first step waits for a transfer)
+        nxt = self.chunk_prefetched if getattr(self, "chunk_prefetched", None) is not None else issue(0)
+        self.chunk_prefetched = None
         for c in range(K):
             now = nxt
+            # queue the next pulls BEFORE handing this piece out: the operations the consumer runs on it block the host
             if c + 1 < K:
                 nxt = issue(c + 1)
-            yield now
+            elif self.prefetch_next_step:
+                self.chunk_prefetched = issue(0)
+            yield now[0], now[1]
             done = torch.cuda.Event()
             done.record(cur)
-            self.chunk_done[c & 1] = done
+            self.chunk_done[now[2]] = done
