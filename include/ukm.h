@@ -150,7 +150,13 @@ int ukm_union(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_sp
 /* inter.go:188-286, iterated in file order; flags: UKM_F_TAXID | UKM_F_MIX_TAXID. */
 int ukm_inter(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_span* out);
 /* diff.go:136-146,341-515 + `-s` emit 566-594; in[0] sorted; subjects sorted or not
- * (in[i].sorted == 0: sorted on the device first).  flags: UKM_F_TAXID | UKM_F_COMPARE_TAXID. */
+ * (in[i].sorted == 0: sorted on the device first).  flags: UKM_F_TAXID | UKM_F_COMPARE_TAXID.
+ * Two deliberate deviations from the reference's behaviour, both reference bugs:
+ *  - an EMPTY sorted subject is skipped ("subtract nothing"); the reference's worker leaves its loop there and
+ *    drops its remaining files (diff.go:387-392, quirk B-5, depends on -j and scheduling);
+ *  - a sorted subject that follows an UNSORTED one is subtracted from the current result; the reference walks
+ *    it against a slice that still holds the keys the unsorted subject removed from its map (diff.go:341-367 vs
+ *    380-435), so removed keys can reappear.  The result here is always file0 minus the union of the subjects. */
 int ukm_diff(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, ukm_span* out);
 /* common.go:220-283,329-354; threshold as computed at common.go:93-105. */
 int ukm_common(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, uint16_t threshold, ukm_span* out);

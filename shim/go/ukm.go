@@ -33,6 +33,15 @@ const (
 	FHashed       = uint(C.UKM_F_HASHED)
 	FCircular     = uint(C.UKM_F_CIRCULAR)
 	FScaled       = uint(C.UKM_F_SCALED)
+	FValidate     = uint(C.UKM_F_VALIDATE)
+	FShard        = uint(C.UKM_F_SHARD)
+)
+
+// Operations of SetopsStream mirror ukm_setop.
+const (
+	OpInter = int(C.UKM_OP_INTER)
+	OpDiff  = int(C.UKM_OP_DIFF)
+	OpUnion = int(C.UKM_OP_UNION)
 )
 
 // Fold modes mirror ukm_fold_mode (sort.go:482-573, util-sort.go:35-190).
@@ -206,6 +215,56 @@ func (x *Ctx) Diff(sets []Set, flags uint) ([]uint64, []uint32, error) {
 	return x.nway(func(in, out *C.ukm_span) C.int {
 		return C.ukm_diff(x.c, in, C.int(len(sets)), C.uint(flags), out)
 	}, sets, len(sets[0].Codes), flags&FTaxid != 0)
+}
+
+// PinnedUint64s returns a []uint64 of n elements in page-locked host memory (ukm_alloc_pinned): host spans in pinned
+// memory are what lets SetopsStream (and Inter / Diff / Union on host sets) overlap uploads, kernels and downloads.
+// The readers fill it in place (reader.ReadCodeWithTaxid in a batch loop); release it with FreePinned.
+func PinnedUint64s(n int) []uint64 {
+	p := C.ukm_alloc_pinned(C.size_t(n) * 8)
+	if p == nil {
+		return nil
+	}
+	return unsafe.Slice((*uint64)(p), n)
+}
+
+// FreePinned releases a slice obtained from PinnedUint64s.
+func FreePinned(s []uint64) {
+	if cap(s) > 0 {
+		C.ukm_free_pinned(unsafe.Pointer(&s[:1][0]))
+	}
+}
+
+// SetopsStream runs any subset of inter / diff / union (ops: OpInter, OpDiff, OpUnion) over the SAME sets in one call:
+// what `unikmer inter`, `unikmer diff` and `unikmer union` over one file list compute (inter.go:188-286,
+// diff.go:136-146 + 380-435, union.go:186-208 + 260-305), with every input byte uploaded once -- the library streams key
+// ranges so that uploads, kernels and downloads overlap.  Keys only.  outs[k] receives the result of ops[k] and must have
+// the capacity of sets[0] (inter, diff) or of all sets together (union); the returned slices are outs[k][:n].
+func (x *Ctx) SetopsStream(sets []Set, ops []int, flags uint, outs [][]uint64) ([][]uint64, error) {
+	in, free := spans(sets)
+	defer free()
+	cops := make([]C.int, len(ops))
+	for i, o := range ops {
+		cops[i] = C.int(o)
+	}
+	n := len(ops)
+	po := (*C.ukm_span)(C.malloc(C.size_t(n) * C.size_t(unsafe.Sizeof(C.ukm_span{}))))
+	defer C.free(unsafe.Pointer(po))
+	osp := unsafe.Slice(po, n)
+	for i := range ops {
+		osp[i] = outSpan(outs[i], nil)
+	}
+	st := C.ukm_setops_stream(x.c, in, C.int(len(sets)), &cops[0], C.int(n), C.uint(flags), po)
+	runtime.KeepAlive(sets)
+	runtime.KeepAlive(outs)
+	if e := x.err(st); e != nil {
+		return nil, e
+	}
+	res := make([][]uint64, n)
+	for i := range ops {
+		res[i] = outs[i][:int(osp[i].n)]
+	}
+	return res, nil
 }
 
 // Common replaces common.go:220-283, 329-354; threshold as computed at common.go:93-105.

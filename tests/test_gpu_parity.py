@@ -665,3 +665,39 @@ def test_large_setop_properties(eng):
     assert bool((u8[1:] > u8[:-1]).all().item())
     assert len(eng.common(files, 1)[0]) == len(u8)
     assert len(eng.common(files, 8)[0]) == len(inter)
+
+
+@pytest.mark.parametrize("variant", ["global", "per_kmer"])
+def test_common_c5_shape(eng, tax, variant):
+    """BASELINE.json configs[4] at 1/100 of its size: `common -n 32` over 64 files x ~1e6 k-mers with TaxId LCA
+    (common.go:93-105 threshold, 220-283 counting + LCA fold, 329-354 select + sort).  SURVEY.md 8(d) generators: universe
+    U(j; 2e6, S=6), file f holds U_j iff bit f of sm64(7 + j); either every file carries one global taxid (the README
+    workflow, README.md:169-171) or every k-mer its own, 1 + sm64(9 + 64 j + f) % 1e4.  (LCA semantics on unknown / merged
+    ids are those of the oracle's restatement: the reference's are unpinned)"""
+    from unikmer_b200 import KmerSet
+    otax, _ = tax
+    N, NF, S, T, R = 2_000_000, 64, 6, 7, 9
+    W = (1 << 62) // N
+    keys = [oracle.member_file(0, N, N, S, T, f) for f in range(NF)]
+    if variant == "global":
+        leaf = [10_000 - f for f in range(NF)]
+        ofiles = [(k, np.full(len(k), t, dtype=np.uint32)) for k, t in zip(keys, leaf)]
+        gsets = [KmerSet(k, None, global_taxid=t) for k, t in zip(keys, leaf)]
+    else:
+        ofiles = []
+        for f, k in enumerate(keys):
+            j = (k // U64(W)).astype(np.uint64)
+            x = (U64(R) + j * U64(64) + U64(f))
+            # sm64 over an array: the same mixer, vectorised
+            z = x + U64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> U64(30))) * U64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> U64(27))) * U64(0x94D049BB133111EB)
+            z = z ^ (z >> U64(31))
+            assert int(z[0]) == oracle.sm64(int(x[0]))
+            ofiles.append((k, (U64(1) + z % U64(10_000)).astype(np.uint32)))
+        gsets = [KmerSet(k, t) for k, t in ofiles]
+    ek, et = oracle.common(ofiles, 32, has_taxid=True, tax=otax)
+    gk, gt = eng.common(gsets, 32, has_taxid=True)
+    assert 0.4 * N < len(ek) < 0.7 * N  # P[Bin(64, 1/2) >= 32] ~ 0.55 of the universe
+    same(gk, ek, f"C5 {variant}: keys")
+    same(gt, et, f"C5 {variant}: taxids")

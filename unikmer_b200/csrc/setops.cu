@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(SO_THREADS) setop_kernel(const SetopArgs p) {
 // ---- keys-only fast path ----------------------------------------------------------------------
 // Same tiling, but the walk is stripped to the bone (no taxids/counts, no per-step validation:
 // UKM_F_VALIDATE checks inputs up front instead) and outputs are staged in a SEPARATE shared
-// buffer so staging needs no barrier against the input slices.  blockIdx.x is the tile id.
+// buffer so staging needs no barrier against the input slices.  Tile ids are tickets (see below).
 template <int OP, int VT>
 __global__ void __launch_bounds__(SO_THREADS, (VT <= 15 ? 3 : 2)) setop_fast_kernel(const SetopArgs p) {
     constexpr int T = SO_THREADS * VT;
@@ -388,9 +388,15 @@ __global__ void __launch_bounds__(SO_THREADS, (VT <= 15 ? 3 : 2)) setop_fast_ker
     __shared__ int s_part[SO_THREADS + 1];
     __shared__ unsigned s_scan[NW + 2];
     __shared__ unsigned long long s_prefix;
+    __shared__ int s_tile;
 
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
+    // Tile ids come from a ticket counter, not from blockIdx.x: the look-back below waits for the tiles BEFORE this one,
+    // and only tickets guarantee that those were handed to CTAs that already run (CUDA does not promise any dispatch
+    // order of blockIdx, and another context may hold part of the GPU).
+    if (tid == 0) s_tile = (int)atomicAdd(p.tile_counter, 1u);
+    __syncthreads();
+    const int tile = s_tile;
     const long long a_lo = p.part[2 * tile], b_lo = p.part[2 * tile + 1];
     const int na = (int)(p.part[2 * tile + 2] - a_lo), nb = (int)(p.part[2 * tile + 3] - b_lo);
     const int hA = slice_offset(p.A, a_lo);
@@ -733,8 +739,11 @@ __global__ void __launch_bounds__(SS_THREADS, TAX ? 6 : 8) setop_search_kernel(c
     __shared__ uint32_t s_ot[TAX ? SS_TILE : 1];
     __shared__ unsigned s_scan[NW + 2];
     __shared__ unsigned long long s_prefix;
+    __shared__ int s_tile;
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
+    if (tid == 0) s_tile = (int)atomicAdd(p.tile_counter, 1u);  // ticket order: the look-back only waits for running tiles
+    __syncthreads();
+    const int tile = s_tile;
     const long long base = (long long)tile * SS_TILE + (long long)tid * SS_ITEMS;
     const long long blo = p.part[tile], bhi = p.part[tile + 1];
     uint64_t a[SS_ITEMS];

@@ -701,7 +701,10 @@ int main(int argc, char** argv) {
                 "usage: unikmer-b200 <count|sort|union|inter|diff|common|split|merge|view|info> [flags] [files]\n"
                 "flags follow unikmer: -o, -C, -c, -i, -I, --max-taxid, --data-dir, --verbose, --device;\n"
                 "  count: -k -K -H -s --circular -D -W -t   sort: -u -d   union: -s   inter: -m\n"
-                "  diff: -s -t   common: -n -p -m   split: -O -m -u -d   merge: -D -u -d   view: -t -N\n");
+                "  diff: -s -t   common: -n -p -m   split: -O -m -u -d   merge: -D -u -d   view: -t -N\n\n"
+                "NOTE: the .unik v5 byte layout used here is restated from memory of shenwei356/unik v5.0.1 (its source is not\n"
+                "part of the reference tree): files are self-consistent, interchange with files written by the real unikmer\n"
+                "is UNVERIFIED (description length field, reserved header block, taxid-length byte; see host/unik.hpp).\n");
         return argc < 2 ? 1 : 0;
     }
     const std::string cmd = argv[1];
