@@ -118,9 +118,16 @@ def cpu_pass(universe: int, threads: int):
 
 def cpu_baseline(sample_universe: int):
     threads = os.cpu_count() or 1
+    # the port's speed at three sample sizes brackets how it moves with the size (the GPU arm runs universe 1e9: the
+    # hash-map union only gets slower as its table outgrows the caches, the two-pointer loops stay flat)
+    by_size = {}
+    for uni in (sample_universe // 4, sample_universe // 2):
+        t_, (a_, b_, c_), _ = cpu_pass(uni, threads)
+        by_size[f"{uni:.1e}"] = {"kmers_per_s": 3 * t_ / (a_ + b_ + c_), "inter": t_ / a_, "diff": t_ / b_, "union": t_ / c_}
     total, (ti, td, tu), sizes = cpu_pass(sample_universe, threads)
     secs = ti + td + tu
-    return {"value": 3 * total / secs, "unit": UNIT, "cores": threads, "kind": "port",
+    by_size[f"{sample_universe:.1e}"] = {"kmers_per_s": 3 * total / secs, "inter": total / ti, "diff": total / td, "union": total / tu}
+    return {"value": 3 * total / secs, "unit": UNIT, "cores": threads, "kind": "port", "by_sample_universe": by_size,
             "sample": f"C3 scaled to universe {sample_universe:.0e} (8 files x ~{sample_universe // 2:.1e} k-mers): one inter+diff+union pass, "
                       f"{secs:.1f} s (inter {ti:.2f} s, diff {td:.2f} s, union {tu:.2f} s); C restatement of the Go algorithms "
                       f"(hash-map union, two-pointer inter/diff; single goroutine each, the sort in union/diff uses {threads} threads)",
@@ -167,8 +174,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--universe", type=float, default=1e9, help="universe size N (files hold ~N/2 k-mers each)")
-    ap.add_argument("--ref-universe", type=float, default=4e7, help="sample universe for the CPU arm")
-    ap.add_argument("--cpu-universe", type=float, default=2e7, help="sample universe for the cpu_baseline object")
+    ap.add_argument("--ref-universe", type=float, default=8e7, help="sample universe for the CPU arm (about 22 s per step on 16 host threads)")
+    ap.add_argument("--cpu-universe", type=float, default=4e7, help="largest sample universe for the cpu_baseline object (also run at 1/2 and 1/4)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)

@@ -60,6 +60,27 @@ def main():
             os.environ.pop("UKM_SORT_CFG", None)
             os.environ.pop("UKM_SORT_MATCH", None)
             del src, work
+        if "cub" in what:
+            # YARDSTICK ONLY: cub::DeviceRadixSort on the same keys (tools/yardstick/libcubyard.so, never part of libukm.so)
+            import ctypes as C
+            yl = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "yardstick", "libcubyard.so"))
+            yl.cub_sort_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.POINTER(C.c_size_t)]
+            src = eng.synth_random_keys(0, n, 2)
+            dst = torch.empty_like(src)
+            need = C.c_size_t(0)
+            assert yl.cub_sort_u64(src.data_ptr(), dst.data_ptr(), n, 0, 62, stream.cuda_stream, None, 0, C.byref(need)) == 0
+            temp = torch.empty(need.value + 256, dtype=torch.uint8, device="cuda")
+
+            def run_cub():
+                r = yl.cub_sort_u64(src.data_ptr(), dst.data_ptr(), n, 0, 62, stream.cuda_stream, temp.data_ptr(), temp.numel(), None)
+                assert r == 0, r
+            ms = timed(stream, run_cub)
+            ok = bool((dst[1:] >= dst[:-1]).all().item())
+            print(json.dumps({"bench": "cub_DeviceRadixSort_u64_YARDSTICK", "n": n, "bits": 62, "ms": ms, "keys_per_s": n / ms * 1e3,
+                              "GBps_136B": 136 * n / ms / 1e6, "sorted": ok, "temp_bytes": need.value,
+                              "note": "library sort, out of place, no input copy; comparison only, never on the product path"}), flush=True)
+            del src, dst, temp
         if "setops" in what:
             U = n
             files = [eng.synth_member_file(0, U, U, 3, 4, f).clone() for f in range(8)]
