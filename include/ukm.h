@@ -168,7 +168,9 @@ int ukm_common(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, uint1
  * key space is cut into ranges (all three are key-local), the slices of range c+1 are uploaded while the operations
  * run on range c and the results of range c-1 are downloaded.  outs[k] receives the result of ops[k]; results are
  * exactly those of ukm_inter / ukm_diff / ukm_union on the whole files (the whole-file rules -- empty first file,
- * empty later file -- are applied on the file sizes).  Keys only (flags: 0 or UKM_F_VALIDATE); inputs all HOST /
+ * empty later file -- are applied on the file sizes).  When both inter and diff are asked for they share ONE pass over
+ * the inputs (after the first subject every key of file 0 can only still belong to one of the two results).
+ * Keys only (flags: 0, UKM_F_VALIDATE, UKM_F_SHARD for device-resident key-range slices); inputs all HOST /
  * HOST_PINNED (pinned memory is what lets the copies overlap: ukm_alloc_pinned) or all DEVICE (then nothing is
  * streamed and the call is the three plain calls).  ukm_inter / ukm_diff / ukm_union take the same streamed path
  * on their own when every input is in host memory. */

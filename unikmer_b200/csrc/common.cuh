@@ -193,6 +193,9 @@ int ukm_launch_coop(ukm_ctx* ctx, K kern, int grid, int threads, size_t smem, A&
     return UKM_OK;
 }
 
+int ukm_nfilter_both(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outI, size_t* n_i, uint64_t* outD,
+                     size_t* n_d, bool* declined);
+
 static inline int ukm_grid_for(size_t work, int per_block, int sm_count, int max_per_sm = 32) {
     size_t g = (work + per_block - 1) / per_block;
     size_t cap = (size_t)sm_count * max_per_sm;

@@ -29,7 +29,7 @@ constexpr int NF_WARPS = 8;                       // consumer warps per CTA
 constexpr int NF_THREADS = NF_WARPS * 32 + 32;    // + the loader warp (warp 0)
 constexpr int NF_S0 = 64;                         // partition: every NF_S0-th boundary is searched in the whole file first
 
-enum { NFOP_INTER = 0, NFOP_DIFF = 1 };
+enum { NFOP_INTER = 0, NFOP_DIFF = 1, NFOP_BOTH = 2 };  // BOTH: inter and diff of the same files in one pass
 
 // ---------------------------------------------------------------------------------------------------
 // partition: bounds[t].pos[f] = first element of file f that belongs to tile t; bounds[num_tiles] = the end
@@ -87,6 +87,7 @@ struct NfArgs {
     NwFiles F;
     const NwBound* bounds;
     unsigned long long* masks;  // one word per SUB keys of file 0: bit j = key j of the group survives
+    unsigned long long* masks2; // NFOP_BOTH: masks = survivors of inter, masks2 = survivors of diff
     int num_tiles;
     int null_mode;  // measurement aids (UKM_MEASURE builds, results NOT valid): 1 = consumers do no work, 2 = also no loads, 3 = narrowing only
     int* err;
@@ -247,9 +248,13 @@ __device__ __forceinline__ int nf_rank(uint32_t seg, int n, uint64_t x, int lg) 
     return n > 0 ? (int)((pp - seg) >> 3) + (nf_lds(pp) < x ? 1 : 0) : 0;
 }
 
+// OP = NFOP_BOTH computes inter and diff together: after file 1 every key is a candidate of exactly ONE of them (found: it
+// can only still be in the intersection, not found: only in the difference), so the later files cost one extra dense round
+// instead of a second pass over all inputs.  *type gets the candidates' kind (bit set: inter); the survivors of inter are
+// alive & type, those of diff alive & ~type.
 template <int OP, int SUB>
 __device__ __forceinline__ unsigned long long nf_tile_fast(const uint64_t* slot, const NfGeom& g, uint8_t* list, int w, int cnt, int nf,
-                                                           unsigned lane, bool narrow_only) {
+                                                           unsigned lane, bool narrow_only, unsigned long long* type) {
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = lanemask_lt();
     const uint32_t slot_a = smem_u32(slot);
@@ -276,6 +281,7 @@ __device__ __forceinline__ unsigned long long nf_tile_fast(const uint64_t* slot,
     }
     unsigned alo = cnt >= 32 ? FULL : ((1u << cnt) - 1u);
     unsigned ahi = (SUB > 32 && cnt > 32) ? (cnt >= 64 ? FULL : ((1u << (cnt - 32)) - 1u)) : 0u;
+    unsigned tlo = 0, thi = 0;  // NFOP_BOTH: the inter candidates
     if (narrow_only) return ((unsigned long long)ahi << 32) | alo;
     // ---- file 1: every key is still there, the lane takes its own keys ----
     int f = 1;
@@ -291,10 +297,22 @@ __device__ __forceinline__ unsigned long long nf_tile_fast(const uint64_t* slot,
         } else {
             fd0 = nf_find(seg, n, x0, lgmax);
         }
-        alo &= ~__ballot_sync(FULL, OP == NFOP_INTER ? !fd0 : fd0);
-        if (SUB > 32) ahi &= ~__ballot_sync(FULL, OP == NFOP_INTER ? !fd1 : fd1);
+        if (OP == NFOP_BOTH) {
+            tlo = __ballot_sync(FULL, fd0);
+            if (SUB > 32) thi = __ballot_sync(FULL, fd1);
+        } else {
+            alo &= ~__ballot_sync(FULL, OP == NFOP_INTER ? !fd0 : fd0);
+            if (SUB > 32) ahi &= ~__ballot_sync(FULL, OP == NFOP_INTER ? !fd1 : fd1);
+        }
         f = 2;
     }
+    // a survivor leaves when a file decides against it: inter candidates on a miss, diff candidates on a hit
+    auto drops = [&](unsigned ix, bool found) -> bool {
+        if (OP == NFOP_INTER) return !found;
+        if (OP == NFOP_DIFF) return found;
+        const bool is_inter = ((ix < 32 ? tlo >> ix : thi >> (ix - 32)) & 1u) != 0;
+        return is_inter ? !found : found;
+    };
     // ---- the other files: survivors are re-listed every round; few survivors take several files per round ----
     const uint32_t list_a = smem_u32(list);
     while (f < nf && (alo | ahi)) {
@@ -314,11 +332,11 @@ __device__ __forceinline__ unsigned long long nf_tile_fast(const uint64_t* slot,
             asm volatile("ld.shared.u8 %0, [%1];" : "=r"(i1) : "r"(list_a + (v1 ? lane + 32 : lane)));
             bool fd0, fd1;
             nf_find2(seg, n, nf_lds(f0a + i0 * 8u), nf_lds(f0a + i1 * 8u), lgmax, &fd0, &fd1);
-            if (OP == NFOP_INTER ? !fd0 : fd0) {
+            if (drops(i0, fd0)) {
                 if (i0 < 32) klo |= 1u << i0;
                 else khi |= 1u << (i0 - 32);
             }
-            if (v1 && (OP == NFOP_INTER ? !fd1 : fd1)) {
+            if (v1 && drops(i1, fd1)) {
                 if (i1 < 32) klo |= 1u << i1;
                 else khi |= 1u << (i1 - 32);
             }
@@ -335,7 +353,7 @@ __device__ __forceinline__ unsigned long long nf_tile_fast(const uint64_t* slot,
             unsigned ix;
             asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ix) : "r"(list_a + (valid ? si : 0)));
             const bool fd = nf_find(seg, n, nf_lds(f0a + ix * 8u), lgmax);
-            if (valid && (OP == NFOP_INTER ? !fd : fd)) {
+            if (valid && drops(ix, fd)) {
                 if (ix < 32) klo = 1u << ix;
                 else khi = 1u << (ix - 32);
             }
@@ -345,17 +363,25 @@ __device__ __forceinline__ unsigned long long nf_tile_fast(const uint64_t* slot,
         if (SUB > 32) ahi &= ~__reduce_or_sync(FULL, khi);
         __syncwarp();  // the list is rewritten in the next round
     }
+    if (OP == NFOP_BOTH) *type = ((unsigned long long)thi << 32) | tlo;
     return ((unsigned long long)ahi << 32) | alo;
 }
 
 // ---- the general path of a warp: some segment of the tile stayed in global memory ------------------------------
 template <int OP, int SUB>
 __device__ __noinline__ unsigned long long nf_tile_generic(const uint64_t* slot, const NfGeom& g, const uint64_t* const* s_fk, NfSub* sub,
-                                                           uint8_t* list, int w, int cnt, int nf, unsigned lane) {
+                                                           uint8_t* list, int w, int cnt, int nf, unsigned lane, unsigned long long* type) {
     const unsigned lt = lanemask_lt();
     const int n0t = g.n[0];
     unsigned alo = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
     unsigned ahi = (SUB > 32 && cnt > 32) ? (cnt >= 64 ? 0xffffffffu : ((1u << (cnt - 32)) - 1u)) : 0u;
+    unsigned tlo = 0, thi = 0;  // NFOP_BOTH: the inter candidates (found in file 1)
+    auto drops = [&](unsigned ix, bool found) -> bool {
+        if (OP == NFOP_INTER) return !found;
+        if (OP == NFOP_DIFF) return found;
+        const bool is_inter = ((ix < 32 ? tlo >> ix : thi >> (ix - 32)) & 1u) != 0;
+        return is_inter ? !found : found;
+    };
     const uint64_t* f0 = slot + g.off[0] + w * SUB;
     // ---- narrow every segment to this warp's key range: lanes 0..7 the lower end, lanes 8..15 the upper end ----
     {
@@ -398,8 +424,13 @@ __device__ __noinline__ unsigned long long nf_tile_generic(const uint64_t* slot,
                 fd0 = nf_contains<long long>(seg, sn, x0);
                 if (SUB > 32 && cnt > 32) fd1 = nf_contains<long long>(seg, sn, x1);
             }
-            if (OP == NFOP_INTER ? !fd0 : fd0) klo = 1u << lane;
-            if (OP == NFOP_INTER ? !fd1 : fd1) khi = 1u << lane;
+            if (OP == NFOP_BOTH) {
+                tlo = __ballot_sync(0xffffffffu, fd0);
+                thi = __ballot_sync(0xffffffffu, fd1);
+            } else {
+                if (OP == NFOP_INTER ? !fd0 : fd0) klo = 1u << lane;
+                if (OP == NFOP_INTER ? !fd1 : fd1) khi = 1u << lane;
+            }
             f += 1;
         } else {
             if (alo >> lane & 1u) list[__popc(alo & lt)] = (uint8_t)lane;
@@ -420,11 +451,11 @@ __device__ __noinline__ unsigned long long nf_tile_generic(const uint64_t* slot,
                     fd0 = nf_contains<long long>(seg, sn, f0[i0]);
                     if (a > 32) fd1 = nf_contains<long long>(seg, sn, f0[i1]);
                 }
-                if ((int)lane < a && (OP == NFOP_INTER ? !fd0 : fd0)) {
+                if ((int)lane < a && drops((unsigned)i0, fd0)) {
                     if (i0 < 32) klo |= 1u << i0;
                     else khi |= 1u << (i0 - 32);
                 }
-                if ((int)lane + 32 < a && (OP == NFOP_INTER ? !fd1 : fd1)) {
+                if ((int)lane + 32 < a && drops((unsigned)i1, fd1)) {
                     if (i1 < 32) klo |= 1u << i1;
                     else khi |= 1u << (i1 - 32);
                 }
@@ -440,7 +471,7 @@ __device__ __noinline__ unsigned long long nf_tile_generic(const uint64_t* slot,
                     bool fd;
                     if (g.n[ff] >= 0) fd = nf_contains<int>(slot + g.off[ff] + (int)slo, (int)sn, f0[ix]);
                     else fd = nf_contains<long long>(s_fk[ff] + g.gpos[ff] + slo, sn, f0[ix]);
-                    if (OP == NFOP_INTER ? !fd : fd) {
+                    if (drops((unsigned)ix, fd)) {
                         if (ix < 32) klo |= 1u << ix;
                         else khi |= 1u << (ix - 32);
                     }
@@ -452,6 +483,7 @@ __device__ __noinline__ unsigned long long nf_tile_generic(const uint64_t* slot,
         if (SUB > 32) ahi &= ~__reduce_or_sync(0xffffffffu, khi);
         __syncwarp();  // the list is rewritten in the next round
     }
+    if (OP == NFOP_BOTH) *type = ((unsigned long long)thi << 32) | tlo;
     return ((unsigned long long)ahi << 32) | alo;
 }
 
@@ -595,13 +627,20 @@ __global__ void __launch_bounds__(NF_THREADS, MINB) nfilter_kernel(const NfArgs 
         const NfGeom& g = s_geom[s];
         int cnt = g.n[0] - w * SUB;
         cnt = cnt < 0 ? 0 : (cnt > SUB ? SUB : cnt);
-        unsigned long long alive = 0;
+        unsigned long long alive = 0, type = 0;
         if (cnt > 0 && p.null_mode != 2) {
             if (p.null_mode == 1) alive = cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull);
-            else if (g.all_smem) alive = nf_tile_fast<OP, SUB>(slot, g, s_list[w], w, cnt, nf, lane, p.null_mode == 3);
-            else alive = nf_tile_generic<OP, SUB>(slot, g, s_fk, s_sub[w], s_list[w], w, cnt, nf, lane);
+            else if (g.all_smem) alive = nf_tile_fast<OP, SUB>(slot, g, s_list[w], w, cnt, nf, lane, p.null_mode == 3, &type);
+            else alive = nf_tile_generic<OP, SUB>(slot, g, s_fk, s_sub[w], s_list[w], w, cnt, nf, lane, &type);
         }
-        if (lane == 0) p.masks[(size_t)tile * NF_WARPS + w] = alive;
+        if (lane == 0) {
+            if (OP == NFOP_BOTH) {
+                p.masks[(size_t)tile * NF_WARPS + w] = alive & type;
+                p.masks2[(size_t)tile * NF_WARPS + w] = alive & ~type;
+            } else {
+                p.masks[(size_t)tile * NF_WARPS + w] = alive;
+            }
+        }
         __syncwarp();  // every lane is past its reads of the slot
         if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
@@ -728,8 +767,10 @@ int nf_env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+// OP = NFOP_BOTH: outK / n_out = inter, outK2 / n_out2 = diff
 template <int OP, int SUB, int CAP, int SLOTS, int MINB>
-int launch_nfilter(ukm_ctx* ctx, NfArgs a, NfPartArgs pa, ukm_tmp& tmp, const uint64_t* F0, uint64_t* outK, size_t* n_out) {
+int launch_nfilter(ukm_ctx* ctx, NfArgs a, NfPartArgs pa, ukm_tmp& tmp, const uint64_t* F0, uint64_t* outK, size_t* n_out,
+                   uint64_t* outK2, size_t* n_out2) {
     using SH = NfShape<SUB, CAP>;
     constexpr size_t smem = (size_t)SLOTS * SH::SLOT_E * 8;
     auto kern = nfilter_kernel<OP, SUB, CAP, SLOTS, MINB>;
@@ -744,8 +785,8 @@ int launch_nfilter(ukm_ctx* ctx, NfArgs a, NfPartArgs pa, ukm_tmp& tmp, const ui
     unsigned long long* d_masks = nullptr;
     unsigned long long* d_sums = nullptr;
     UKM_TRY(tmp.alloc(&d_bounds, (size_t)num_tiles + 1));
-    UKM_TRY(tmp.alloc(&d_masks, n_masks));
-    UKM_TRY(tmp.alloc(&d_sums, (size_t)nb + 1));
+    UKM_TRY(tmp.alloc(&d_masks, n_masks * (OP == NFOP_BOTH ? 2 : 1)));
+    UKM_TRY(tmp.alloc(&d_sums, ((size_t)nb + 1) * (OP == NFOP_BOTH ? 2 : 1)));
     {
         const int n0 = num_tiles / NF_S0 + 2;
         nfilter_partition_kernel<<<(n0 + 63) / 64, 64, 0, ctx->stream>>>(pa, d_bounds, NF_S0, 0);
@@ -755,6 +796,7 @@ int launch_nfilter(ukm_ctx* ctx, NfArgs a, NfPartArgs pa, ukm_tmp& tmp, const ui
     }
     a.bounds = d_bounds;
     a.masks = d_masks;
+    a.masks2 = d_masks + n_masks;
     a.num_tiles = num_tiles;
     int grid = per_sm * ctx->sm_count;
     if (grid > num_tiles) grid = num_tiles;
@@ -767,8 +809,19 @@ int launch_nfilter(ukm_ctx* ctx, NfArgs a, NfPartArgs pa, ukm_tmp& tmp, const ui
     nfilter_gather_kernel<SUB><<<nb, NG_THREADS, 0, ctx->stream>>>(d_masks, n_masks, F0, d_sums, outK);
     UKM_LAUNCHED(ctx);
     UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_sums + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (OP == NFOP_BOTH) {
+        unsigned long long* d_sums2 = d_sums + nb + 1;
+        nfilter_count_kernel<<<nb, NG_THREADS, 0, ctx->stream>>>(a.masks2, n_masks, d_sums2);
+        UKM_LAUNCHED(ctx);
+        nfilter_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_sums2, nb, d_sums2 + nb);
+        UKM_LAUNCHED(ctx);
+        nfilter_gather_kernel<SUB><<<nb, NG_THREADS, 0, ctx->stream>>>(a.masks2, n_masks, F0, d_sums2, outK2);
+        UKM_LAUNCHED(ctx);
+        UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 1, d_sums2 + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *n_out = (size_t)ctx->h_scratch[0];
+    if (OP == NFOP_BOTH) *n_out2 = (size_t)ctx->h_scratch[1];
     tmp.free_now(d_bounds);
     tmp.free_now(d_masks);
     tmp.free_now(d_sums);
@@ -777,16 +830,16 @@ int launch_nfilter(ukm_ctx* ctx, NfArgs a, NfPartArgs pa, ukm_tmp& tmp, const ui
 
 template <int OP>
 int launch_nfilter_sub(ukm_ctx* ctx, int sub, const NfArgs& a, const NfPartArgs& pa, ukm_tmp& tmp, const uint64_t* F0, uint64_t* outK,
-                       size_t* n_out) {
+                       size_t* n_out, uint64_t* outK2 = nullptr, size_t* n_out2 = nullptr) {
     // slot capacity x ring depth x CTAs per SM: 2 x 36 KB x 3 (default: C3 inter 10.0 ms on B200); UKM_NFILTER_CFG = 1: 4 x 27 KB x 2
     // (19.5 ms: tiles of 256 file-0 keys), 2: 3 x 36 KB x 2 (11.4 ms: 16 instead of 24 consumer warps per SM) -- A/B runs
     const int cfg = nf_env_int("UKM_NFILTER_CFG", 0);
 #define NF_LAUNCH(CAP, SLOTS, MINB)                                                                                   \
     switch (sub) {                                                                                                    \
-        case 64: return launch_nfilter<OP, 64, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out);                    \
-        case 32: return launch_nfilter<OP, 32, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out);                    \
-        case 16: return launch_nfilter<OP, 16, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out);                    \
-        default: return launch_nfilter<OP, 8, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out);                     \
+        case 64: return launch_nfilter<OP, 64, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out, outK2, n_out2);    \
+        case 32: return launch_nfilter<OP, 32, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out, outK2, n_out2);    \
+        case 16: return launch_nfilter<OP, 16, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out, outK2, n_out2);    \
+        default: return launch_nfilter<OP, 8, CAP, SLOTS, MINB>(ctx, a, pa, tmp, F0, outK, n_out, outK2, n_out2);     \
     }
     if (cfg == 1) { NF_LAUNCH(3392, 4, 2) }
     if (cfg == 2) { NF_LAUNCH(4576, 3, 2) }
@@ -846,5 +899,45 @@ int ukm_nfilter(ukm_ctx* ctx, bool inter, const uint64_t* const* keys, const siz
         else UKM_TRY(launch_nfilter_sub<NFOP_DIFF>(ctx, sub, a, pa, tmp, keys[0], outK, n_out));
     }
     if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes += (double)*n_out * 8.0;
+    return UKM_OK;
+}
+
+// inter AND diff of the same files in one pass (every input read once for the two results): outI / outD capacity >= n[0].
+int ukm_nfilter_both(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outI, size_t* n_i, uint64_t* outD,
+                     size_t* n_d, bool* declined) {
+    *declined = false;
+    *n_i = *n_d = 0;
+    if (nf < 2 || nf > NW_MAX) return ukm_fail(ctx, UKM_E_ARG, "nfilter: 2..8 inputs");
+    if (n[0] == 0) return UKM_OK;
+    NfArgs a;
+    NfPartArgs pa;
+    long long total = 0;
+    for (int f = 0; f < NW_MAX; ++f) {
+        a.F.k[f] = f < nf ? keys[f] : nullptr;
+        a.F.n[f] = f < nf ? (long long)n[f] : 0;
+        total += a.F.n[f];
+    }
+    a.F.nf = nf;
+    a.err = ctx->d_err;
+    a.null_mode = 0;
+    pa.F = a.F;
+    pa.n0 = (long long)n[0];
+    const double ratio = (double)total / (double)n[0];
+    const double cap = nf_env_int("UKM_NFILTER_CFG", 0) == 1 ? 3392.0 : 4576.0;
+    int sub = 0;
+    for (int c = 64; c >= 8; c >>= 1)
+        if ((double)(NF_WARPS * c) * ratio <= 0.9 * cap) { sub = c; break; }
+    const int force = nf_env_int("UKM_NFILTER_SUB", 0);
+    if (force == 64 || force == 32 || force == 16 || force == 8) sub = force;
+    if (sub == 0) {
+        *declined = true;
+        return UKM_OK;
+    }
+    ukm_tmp tmp(ctx);
+    {
+        ukm_stat_scope st(ctx, "setop_inter_diff_nway", (double)total * 8.0);  // the inputs once (+ both outputs, added below)
+        UKM_TRY(launch_nfilter_sub<NFOP_BOTH>(ctx, sub, a, pa, tmp, keys[0], outI, n_i, outD, n_d));
+    }
+    if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes += (double)(*n_i + *n_d) * 8.0;
     return UKM_OK;
 }

@@ -1411,6 +1411,46 @@ int run_tree(ukm_ctx* ctx, int op, const ukm_span* in, int n_in, unsigned flags,
 }
 
 
+// inter AND diff of the same sorted device-resident spans in ONE pass (nfilter.cu, NFOP_BOTH): after the first subject
+// every key of file 0 is a candidate of exactly one of the two results, so both come out of one read of the inputs.
+// `shard`: the spans are key-range slices (an empty slice empties that range's intersection and subtracts nothing).
+// *done = false: the fused pass does not apply (more than eight files, an empty WHOLE file -- the whole-file rules of
+// inter differ --, file 0 far sparser than the subjects); the caller runs the two operations one after the other.
+int fused_inter_diff(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, bool shard, ukm_span* out_i, ukm_span* out_d,
+                     bool* done) {
+    *done = false;
+    if (!ukm_nfilter_enabled() || n_in < 2 || n_in > NW_FANIN) return UKM_OK;
+    for (int f = 0; f < n_in; ++f) {
+        if (in[f].where != UKM_DEVICE || !in[f].sorted) return UKM_OK;
+        if (!shard && in[f].n == 0) return UKM_OK;
+    }
+    const uint64_t* ks[NW_FANIN];
+    size_t ns[NW_FANIN];
+    for (int f = 0; f < n_in; ++f) {
+        ks[f] = in[f].keys;
+        ns[f] = in[f].n;
+        if ((flags & UKM_F_VALIDATE) && in[f].n > 1) UKM_TRY(ukm_dev_check_sorted_unique(ctx, in[f].keys, in[f].n));
+    }
+    ukm_tmp tmp(ctx);
+    const size_t cap = in[0].n;
+    uint64_t *d_i = nullptr, *d_d = nullptr;
+    const bool direct_i = out_i->where == UKM_DEVICE && out_i->cap >= cap && out_i->keys;
+    const bool direct_d = out_d->where == UKM_DEVICE && out_d->cap >= cap && out_d->keys;
+    if (direct_i) d_i = out_i->keys;
+    else UKM_TRY(tmp.alloc(&d_i, cap + 2));
+    if (direct_d) d_d = out_d->keys;
+    else UKM_TRY(tmp.alloc(&d_d, cap + 2));
+    size_t n_i = 0, n_d = 0;
+    bool declined = false;
+    UKM_TRY(ukm_nfilter_both(ctx, ks, ns, n_in, d_i, &n_i, d_d, &n_d, &declined));
+    if (declined) return UKM_OK;
+    UKM_TRY(ukm_check_dev_error(ctx, "ukm_setops_stream(inter+diff)"));
+    UKM_TRY(ukm_deliver(ctx, d_i, nullptr, n_i, out_i));
+    UKM_TRY(ukm_deliver(ctx, d_d, nullptr, n_d, out_d));
+    *done = true;
+    return UKM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // streamed operations on HOST inputs: every input byte crosses PCIe once, uploads / kernels / downloads overlap
 // ---------------------------------------------------------------------------------------------------
@@ -1471,6 +1511,11 @@ int stream_run(ukm_ctx* ctx, const ukm_span* in, int n_in, const int* ops, int n
     for (int k = 0; k < n_ops; ++k)
         if (ops[k] == UKM_OP_INTER && in[0].n == 0)
             return ukm_fail(ctx, UKM_E_PANIC, "ukm_setops_stream: first input is empty (inter.go:208 panics)");
+    int k_inter = -1, k_diff = -1;  // the first inter and the first diff of the call: candidates for the fused pass
+    for (int k = n_ops - 1; k >= 0; --k) {
+        if (ops[k] == UKM_OP_INTER) k_inter = k;
+        if (ops[k] == UKM_OP_DIFF) k_diff = k;
+    }
     // buffers: the largest range decides
     size_t max_in = 0, max_f0 = 0;
     for (int c = 0; c < K; ++c) {
@@ -1536,7 +1581,24 @@ int stream_run(ukm_ctx* ctx, const ukm_span* in, int n_in, const int* ops, int n
             pos += (n + 1) & ~(size_t)1;
         }
         size_t n_res[8] = {0};
+        bool have[8] = {false};
+        if (k_inter >= 0 && k_diff >= 0 && n_inter == n_in) {
+            // inter and diff of the range in one pass over its slices
+            ukm_span oi, od;
+            memset(&oi, 0, sizeof oi);
+            memset(&od, 0, sizeof od);
+            oi.keys = d_out[q][k_inter]; oi.cap = cap_out[k_inter]; oi.where = UKM_DEVICE;
+            od.keys = d_out[q][k_diff]; od.cap = cap_out[k_diff]; od.where = UKM_DEVICE;
+            bool done = false;
+            status = fused_inter_diff(ctx, dsp.data(), n_in, flags, true, &oi, &od, &done);
+            if (status == UKM_OK && done) {
+                n_res[k_inter] = oi.n;
+                n_res[k_diff] = od.n;
+                have[k_inter] = have[k_diff] = true;
+            }
+        }
         for (int k = 0; k < n_ops && status == UKM_OK; ++k) {
+            if (have[k]) continue;
             ukm_span o;
             memset(&o, 0, sizeof o);
             o.keys = d_out[q][k];
@@ -1653,10 +1715,25 @@ extern "C" int ukm_setops_stream(ukm_ctx* ctx, const ukm_span* in, int n_in, con
     }
     if (!host && !dev) return ukm_fail(ctx, UKM_E_ARG, "ukm_setops_stream: all inputs must live in the same memory space");
     if (host && sorted) return stream_run(ctx, in, n_in, ops, n_ops, flags, outs);
-    // device-resident inputs (nothing to stream) or an unsorted diff subject: the plain calls, one after the other
+    // device-resident inputs (nothing to stream) or an unsorted diff subject: the plain calls, one after the other --
+    // except that inter and diff of the same files share one pass over the inputs
+    bool have[8] = {false};
+    {
+        int k_inter = -1, k_diff = -1;
+        for (int k = n_ops - 1; k >= 0; --k) {
+            if (ops[k] == UKM_OP_INTER) k_inter = k;
+            if (ops[k] == UKM_OP_DIFF) k_diff = k;
+        }
+        if (dev && k_inter >= 0 && k_diff >= 0) {
+            bool done = false;
+            UKM_TRY(fused_inter_diff(ctx, in, n_in, flags, (flags & UKM_F_SHARD) != 0, &outs[k_inter], &outs[k_diff], &done));
+            if (done) have[k_inter] = have[k_diff] = true;
+        }
+    }
     for (int k = 0; k < n_ops; ++k) {
+        if (have[k]) continue;
         int r;
-        if (ops[k] == UKM_OP_INTER) r = run_chain(ctx, OP_INTER, in, n_in, flags & UKM_F_VALIDATE, &outs[k], "ukm_setops_stream(inter)");
+        if (ops[k] == UKM_OP_INTER) r = run_chain(ctx, OP_INTER, in, n_in, flags & (UKM_F_VALIDATE | UKM_F_SHARD), &outs[k], "ukm_setops_stream(inter)");
         else if (ops[k] == UKM_OP_DIFF) r = run_chain(ctx, OP_DIFF, in, n_in, flags & UKM_F_VALIDATE, &outs[k], "ukm_setops_stream(diff)");
         else r = run_tree(ctx, OP_UNION, in, n_in, flags & UKM_F_VALIDATE, false, 0, UKM_FOLD_PLAIN, &outs[k], "ukm_setops_stream(union)");
         UKM_TRY(r);

@@ -275,7 +275,8 @@ class Engine:
         self._chk(self.lib.ukm_diff(self.ctx, arr, len(arr), flags, C.byref(out)))
         return self._trim(out, k, t)
 
-    def setops(self, sets: Sequence, ops: Sequence[str] = ("inter", "diff", "union"), outs=None, validate: bool = False):
+    def setops(self, sets: Sequence, ops: Sequence[str] = ("inter", "diff", "union"), outs=None, validate: bool = False,
+               shard: bool = False):
         """Several of `inter` / `diff` / `union` over the same k-mer sets in ONE call (ukm_setops_stream): with host-resident
         sets every input byte crosses PCIe once and uploads, kernels and downloads overlap.  `outs`: one caller-provided
         key buffer per operation (pinned host tensors for full overlap), or None.  Returns one key array per operation."""
@@ -290,7 +291,8 @@ class Engine:
             sp, kb, _ = self._span_out(cap, False, dev, None if outs is None else outs[k])
             spans[k] = sp
             bufs.append(kb)
-        self._chk(self.lib.ukm_setops_stream(self.ctx, arr, len(arr), opc, len(ops), L.F_VALIDATE if validate else 0, spans))
+        flags = (L.F_VALIDATE if validate else 0) | (L.F_SHARD if shard else 0)
+        self._chk(self.lib.ukm_setops_stream(self.ctx, arr, len(arr), opc, len(ops), flags, spans))
         return [b[:int(spans[k].n)] for k, b in enumerate(bufs)]
 
     def common(self, sets: Sequence, threshold: int, has_taxid: bool = False, validate: bool = False):
