@@ -258,9 +258,9 @@ def main():
             ou = torch.empty(total_in + 16, dtype=torch.int64, device=dev)
 
         def step():
-            # ONE call of the C ABI per step (ukm_setops_stream on device spans): inter and diff share one pass over the
-            # inputs (after the first subject a key of file 0 can only still belong to one of the two results), the union
-            # is the single-pass N-way merge; all three results are written in full every step
+            # ONE call of the C ABI per step (ukm_setops_stream on device spans): the single-pass N-way union kernel sees, in
+            # its last merge level, how many files hold every key -- which is all inter (every file) and diff (file 0 only)
+            # need -- so all three results come out of one pass over the inputs; all three are written in full every step
             if world == 1:
                 return tuple(eng.setops([local_files[f] for f in range(N_FILES)], OPS, outs=[oi, od, ou]))
             if pex is None:
@@ -394,6 +394,9 @@ def main():
         kernel_of = {"setop_union_nway": "nway_kernel<UNION> (single-pass 8-way union: TMA tile loads, in-smem merge levels) + its partition",
                      "setop_inter_nway": "nfilter_kernel<INTER> (single-pass 8-way filter over file-0 chunks) + partition + mask gather",
                      "setop_diff_nway": "nfilter_kernel<DIFF> (single-pass 8-way filter over file-0 chunks) + partition + mask gather",
+                     "setop_inter_diff_union_nway": "nway_kernel<UNION> with inter / diff riding along (ONE pass for the three results: the last "
+                                                    "merge level sees how many files hold each key) + its partition",
+                     "setop_mask_gather": "inter / diff masks -> compact results (count / scan / gather)",
                      "setop_inter_diff_nway": "nfilter_kernel<BOTH> (inter AND diff in one pass over file-0 chunks) + partition + mask gathers",
                      "setop_union": "setop_pipe_kernel<UNION> (two-way merge-path passes)",
                      "setop_inter": "setop_pipe_kernel<INTER> + setop_search_kernel (two-way passes in file order)",
@@ -528,8 +531,9 @@ def main():
             "config": {"workload": f"C3: inter+diff+union over 8 sorted duplicate-free files x ~{U // 2:.1e} k=31 uint64 k-mers "
                                    f"(universe {U:.0e}, {total_in} k-mers in); each op reads all inputs",
                        "inputs": "device-resident, 32 GB >> 126 MB L2 (no L2 flush needed)" if U >= 10**8 else "device-resident",
-                       "step": "one C-ABI call (ukm_setops_stream, device spans) per step and rank: inter + diff share one pass over the "
-                               "inputs, union is the single-pass 8-way merge; all three results written in full",
+                       "step": "one C-ABI call (ukm_setops_stream, device spans) per step and rank: union, inter and diff from ONE pass over "
+                               "the inputs (single-pass 8-way merge; inter / diff from the run lengths of its last level); all three "
+                               "results written in full; the same step as three separate calls is reported in three_separate_calls",
                        "parallelism": ("1 GPU" if world == 1 else f"key-range shards x{world}, " +
                                        (f"NVLink peer pulls on the copy engines (CUDA IPC), {args.exchange_chunks} piece(s) per rank and step, double-buffered: "
                                         "the next piece (the next step's first piece after the last one) is pulled while the single-pass N-way "

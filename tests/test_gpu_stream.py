@@ -130,8 +130,9 @@ def test_fused_inter_diff_on_device_spans(eng):
         gi, gd, gu = eng.setops(dev, ("inter", "diff", "union"))
         eng.stats_enable(False)
         st = eng.stats()
-        if nf >= 3:  # two files: file 0 is not sparse enough for the chunk filter's heuristic? it still applies (ratio 2)
-            assert st.get("setop_inter_diff_nway", {}).get("launches") == 1, st
+        if nf >= 3:  # all three results from ONE pass: the union kernel, inter / diff riding along (nway.cu)
+            assert st.get("setop_inter_diff_union_nway", {}).get("launches") == 1, st
+            assert "setop_inter_nway" not in st and "setop_diff_nway" not in st and "setop_union_nway" not in st, st
         same(gi.cpu().numpy().view(U64), oracle.inter(files)[0], f"fused inter nf {nf}")
         same(gd.cpu().numpy().view(U64), oracle.diff(files)[0], f"fused diff nf {nf}")
         same(gu.cpu().numpy().view(U64), oracle.union(files)[0], f"union nf {nf}")
@@ -178,3 +179,44 @@ def test_fused_inter_diff_whole_file_rules_and_shards(eng):
     gi, gd = eng.setops(devm, ("inter", "diff"))
     same(gi.cpu().numpy().view(U64), oracle.inter(many)[0], "inter of 11 files")
     same(gd.cpu().numpy().view(U64), oracle.diff(many)[0], "diff of 11 files")
+
+
+@pytest.mark.parametrize("nf", [3, 4, 5, 7, 8])
+def test_union_with_inter_diff_riding_along(eng, nf):
+    """ukm_setops_stream with all three operations on device spans: ONE pass (nway.cu -- a run of equal keys in the last
+    merge level is as long as the number of files that hold the key: run = nf is the intersection, run = 1 with the key in
+    file 0 the difference).  Sizes that put runs across thread, tile and mask-word seams; distributions with long runs."""
+    import torch
+    r = rng(nf)
+    cases = {f"members {N}": member_files(N, nf) for N in (2_000, 100_000, 3_000_000)}
+    base = np.unique(r.integers(0, 2**64, 500_000, dtype=U64))
+    cases["identical"] = [base.copy() for _ in range(nf)]                       # every run is nf long
+    cases["disjoint"] = [base[q::nf].copy() for q in range(nf)]                 # every run is 1 long
+    cases["file0 subset"] = [base[::3].copy()] + [base.copy() for _ in range(nf - 1)]
+    cases["file0 superset"] = [base.copy()] + [base[q::5].copy() for q in range(nf - 1)]
+    cases["extremes"] = [np.unique(np.concatenate([base[r.random(len(base)) < 0.5], np.array([0, 2**64 - 1], dtype=U64)])) for _ in range(nf)]
+    for name, files in cases.items():
+        dev = [torch.from_numpy(f.view(np.int64)).cuda() for f in files]
+        gi, gd, gu = eng.setops(dev, ("inter", "diff", "union"))
+        same(gu.cpu().numpy().view(U64), oracle.union(files)[0], f"{name}: union")
+        same(gi.cpu().numpy().view(U64), oracle.inter(files)[0], f"{name}: inter")
+        same(gd.cpu().numpy().view(U64), oracle.diff(files)[0], f"{name}: diff")
+
+
+def test_fusion_switch_and_order_of_outputs(eng, monkeypatch):
+    import torch
+    files = member_files(800_000, 8)
+    dev = [torch.from_numpy(f.view(np.int64)).cuda() for f in files]
+    exp = {"inter": oracle.inter(files)[0], "diff": oracle.diff(files)[0], "union": oracle.union(files)[0]}
+    for ops in (("union", "diff", "inter"), ("diff", "union", "inter", "union")):
+        for g, o in zip(eng.setops(dev, ops), ops):
+            same(g.cpu().numpy().view(U64), exp[o], f"{ops}: {o}")
+    monkeypatch.setenv("UKM_FUSE3", "0")  # inter + diff fused (chunk filter), union on its own
+    eng.stats_reset()
+    eng.stats_enable(True)
+    got = eng.setops(dev, ("inter", "diff", "union"))
+    eng.stats_enable(False)
+    st = eng.stats()
+    assert st.get("setop_inter_diff_nway", {}).get("launches") == 1 and st.get("setop_union_nway", {}).get("launches") == 1, st
+    for g, o in zip(got, ("inter", "diff", "union")):
+        same(g.cpu().numpy().view(U64), exp[o], f"UKM_FUSE3=0: {o}")

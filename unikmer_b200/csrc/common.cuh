@@ -193,6 +193,8 @@ int ukm_launch_coop(ukm_ctx* ctx, K kern, int grid, int threads, size_t smem, A&
     return UKM_OK;
 }
 
+int ukm_nway_union3(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out, uint64_t* outI,
+                    size_t* n_i, uint64_t* outD, size_t* n_d, bool* fell_back);
 int ukm_nfilter_both(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outI, size_t* n_i, uint64_t* outD,
                      size_t* n_d, bool* declined);
 

@@ -941,3 +941,25 @@ int ukm_nfilter_both(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n,
     if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes += (double)(*n_i + *n_d) * 8.0;
     return UKM_OK;
 }
+
+// masks (one 64-bit word per 64 keys of F0, bit j = key 64 * word + j is kept) -> compact sorted result.  Shared with the
+// N-way union, whose inter / diff results ride along as such masks (nway.cu).
+int ukm_masks_gather(ukm_ctx* ctx, ukm_tmp& tmp, const unsigned long long* d_masks, size_t n_masks, const uint64_t* F0, uint64_t* outK,
+                     size_t* n_out) {
+    *n_out = 0;
+    if (n_masks == 0) return UKM_OK;
+    const int nb = (int)((n_masks + NG_BLOCK - 1) / NG_BLOCK);
+    unsigned long long* d_sums = nullptr;
+    UKM_TRY(tmp.alloc(&d_sums, (size_t)nb + 1));
+    nfilter_count_kernel<<<nb, NG_THREADS, 0, ctx->stream>>>(d_masks, n_masks, d_sums);
+    UKM_LAUNCHED(ctx);
+    nfilter_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_sums, nb, d_sums + nb);
+    UKM_LAUNCHED(ctx);
+    nfilter_gather_kernel<64><<<nb, NG_THREADS, 0, ctx->stream>>>(d_masks, n_masks, F0, d_sums, outK);
+    UKM_LAUNCHED(ctx);
+    UKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch + 2, d_sums + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    UKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = (size_t)ctx->h_scratch[2];
+    tmp.free_now(d_sums);
+    return UKM_OK;
+}

@@ -96,6 +96,10 @@ struct NwArgs {
     unsigned long long* total_out;
     int num_tiles;
     int null_mode;  // measurement aids for inter / diff (results are NOT valid): UKM_NWAY_NULL=1 tiles do no work, =2 load pipeline only
+    // union only, optional: inter and diff of the same files ride along (one bit per key of file 0, by position: bit set =
+    // the key is in the intersection of all files / in no other file).  NULL = plain union.
+    unsigned long long* mask_i;
+    unsigned long long* mask_d;
     int* err;
 };
 
@@ -224,6 +228,16 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
     __shared__ const uint64_t* s_fk[NW_MAX];
     __shared__ unsigned s_scan[NW + 2];
     __shared__ int s_cnt3[4];  // rotating work-list counters of the inter / diff rounds
+    __shared__ long long s_g0[SLOTS];  // first element of the tile in file 0 (global position)
+    __shared__ unsigned char s_lead[NT];  // leading keys of a thread's range that continue the run of the thread before
+    // inter / diff riding along need file 0's segment of the tile at the last level; with three levels the slot has been
+    // overwritten by then (level 2 writes it), so a copy is kept here when it fits (else: the global array, slow, rare)
+    constexpr int F0CAP = (OP == NWOP_UNION && LEVELS == 3) ? 512 : 1;
+    __shared__ uint64_t s_f0[F0CAP];
+    constexpr int NCAND = OP == NWOP_UNION ? 128 : 1;  // candidate list of a tile (a run of nf or of 1 key)
+    __shared__ uint64_t s_ckey[NCAND];
+    __shared__ unsigned char s_cone[NCAND];
+    __shared__ int s_ncand;
 
     const int G = gridDim.x;
     const int n_my = (p.num_tiles - (int)blockIdx.x + G - 1) / G;  // tiles of this CTA
@@ -294,6 +308,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
                 s_geom[s].n[lane] = n;
                 s_geom[s].off[lane] = base + h;
             }
+            if (lane == 0) s_g0[s] = lo;
             __syncwarp();
             if (lane == 0) {
                 if (OP == NWOP_UNION) nw_build_tables<NWAY, VT>(&s_geom[s]);
@@ -379,6 +394,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
         unsigned emitmask = 0;
         uint64_t outk[VT];
         unsigned off = 0;
+        int last_steps = 0;
         uint64_t* slot = nullptr;
         if (i < n_my) {
             const int s = i % SLOTS, u = i / SLOTS;
@@ -387,11 +403,14 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
                 if (tid == 0) atomicExch(p.err, (int)UKM_E_INTERNAL);
             }
             const NwGeom<NWAY>& g = s_geom[s];
+            if (OP == NWOP_UNION && tid == 0 && p.mask_i) s_ncand = 0;  // read again only after the barriers of the scan
             if constexpr (OP != NWOP_UNION) {
                 emitmask = nw_filter_tile<OP, NT, VT>(slot, g, s_x, s_cnt3, tid, p.F.nf, p.null_mode != 0, outk);
             } else {
             const uint64_t* src = slot;
             uint64_t* dst = s_x;
+            if (LEVELS == 3 && p.mask_i && g.n[0] <= F0CAP)
+                for (int j = tid; j < g.n[0]; j += NT) s_f0[j] = slot[g.off[0] + j];
             // inner levels: plain two-way merges, every pair of runs by its own group of threads
 #pragma unroll
             for (int l = 1; l < LEVELS; ++l) {
@@ -428,10 +447,68 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
                 const uint64_t* B = src + pr.srcB;
                 const int a = nw_merge_path_g(A, pr.lenA, B, pr.lenB, diag);
                 emitmask = nw_walk_unique<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, outk);
+                last_steps = steps > 0 ? steps : 0;
+                // the leading keys that were not emitted continue the run the thread before started
+                if (p.mask_i) s_lead[tid] = (unsigned char)(emitmask ? __ffs(emitmask) - 1 : last_steps);
             }
             }  // union
             unsigned tile_total;
             off = group_excl_scan_u32<NT>((unsigned)__popc(emitmask), (unsigned)tid, s_scan, &tile_total, 1);
+            if constexpr (OP == NWOP_UNION) {
+                if (p.mask_i) {
+                    // inter / diff ride along: a run of equal keys has one key per file that holds it (the inputs are
+                    // duplicate-free), so a run as long as the file count is a key of the intersection, and a run of one
+                    // whose key sits in file 0 is a key of the difference.  Runs are at most nf <= 8 < VT keys long: one that
+                    // starts here can only continue into the NEXT thread (s_lead, published before the scan's barriers).
+                    // The candidates (few: a run of nf or of 1) go to a list; then one thread per candidate finds the key's
+                    // position in file 0 -- the bit to set -- by binary search in file 0's keys of the tile.
+                    const int n0 = g.n[0];
+                    // file 0's keys of the tile: still in the slot (one or two levels), the copy made before level 1 (three
+                    // levels), or -- the copy did not fit -- the global array
+                    const uint64_t* f0 = LEVELS < 3 ? slot + g.off[0] : (n0 <= F0CAP ? s_f0 : s_fk[0] + s_g0[s]);
+                    auto mark = [&](uint64_t x, bool one) {
+                        int lo_ = 0, hi_ = n0;  // lower_bound of x in file 0's segment
+                        while (lo_ < hi_) {
+                            const int mid = (lo_ + hi_) >> 1;
+                            if (f0[mid] < x) lo_ = mid + 1;
+                            else hi_ = mid;
+                        }
+                        if (lo_ < n0 && f0[lo_] == x) {
+                            const unsigned long long idx = (unsigned long long)(s_g0[s] + lo_);
+                            atomicOr((one ? p.mask_d : p.mask_i) + (idx >> 6), 1ull << (idx & 63));
+                        }
+                    };
+                    const int lead_next = tid + 1 < NT ? (int)s_lead[tid + 1] : 0;
+                    const int nfiles = p.F.nf;
+                    // (a warp-uniform loop over the VT positions with ballot-aggregated list appends was measured slower:
+                    // 45.1 against 40.6 ms per C3 call)
+                    unsigned m = emitmask;
+                    while (m) {
+                        const int b0 = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int nxt = m ? __ffs(m) - 1 : last_steps + lead_next;
+                        const int len = nxt - b0;
+                        if (len == nfiles || len == 1) {
+                            uint64_t x = outk[0];
+#pragma unroll
+                            for (int it = 1; it < VT; ++it)
+                                if (it == b0) x = outk[it];
+                            const int pos = atomicAdd(&s_ncand, 1);
+                            if (pos < NCAND) {
+                                s_ckey[pos] = x;
+                                s_cone[pos] = len == 1;
+                            } else {
+                                mark(x, len == 1);  // more candidates than the list holds (files that barely overlap): in place
+                            }
+                        }
+                    }
+                    named_bar_sync(1, NT);  // the list is complete
+                    const int nc = s_ncand < NCAND ? s_ncand : NCAND;
+                    for (int j = tid; j < nc; j += NT) mark(s_ckey[j], s_cone[j] != 0);
+                    // file 0's keys were read from the slot, which the staging below overwrites
+                    if (LEVELS < 3) named_bar_sync(1, NT);
+                }
+            }
             // every consumer is past its reads of the slot (two barriers inside the scan): it may be overwritten
             if (tid == 0) {
                 s_cnt[s] = tile_total;
@@ -515,7 +592,7 @@ int launch_nway_cfg(ukm_ctx* ctx, const NwArgs& a, const NwPartArgs& pa, ukm_tmp
 }
 
 int nway_run(ukm_ctx* ctx, int op, const char* stat_name, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK,
-             size_t* n_out, bool* fell_back) {
+             size_t* n_out, bool* fell_back, unsigned long long* mask_i = nullptr, unsigned long long* mask_d = nullptr) {
     *fell_back = false;
     *n_out = 0;
     if (nf < 2 || nf > NW_MAX) return ukm_fail(ctx, UKM_E_ARG, "nway: 2..8 inputs");
@@ -534,6 +611,8 @@ int nway_run(ukm_ctx* ctx, int op, const char* stat_name, const uint64_t* const*
     a.outK = outK;
     a.err = ctx->d_err;
     a.null_mode = 0;
+    a.mask_i = mask_i;
+    a.mask_d = mask_d;
 #ifdef UKM_MEASURE  // measurement build only (make EXTRA=-DUKM_MEASURE): the null modes produce no valid result
     {
         const char* e = getenv("UKM_NWAY_NULL");
@@ -621,4 +700,30 @@ int ukm_nway_filter(ukm_ctx* ctx, bool inter, const uint64_t* const* keys, const
                     bool* fell_back) {
     return nway_run(ctx, inter ? NWOP_INTER : NWOP_DIFF, inter ? "setop_inter_nway" : "setop_diff_nway", keys, n, nf, outK, n_out,
                     fell_back);
+}
+
+int ukm_masks_gather(ukm_ctx* ctx, ukm_tmp& tmp, const unsigned long long* d_masks, size_t n_masks, const uint64_t* F0, uint64_t* outK,
+                     size_t* n_out);
+
+// union, inter and diff of the same nf (2..8) sorted duplicate-free device arrays from ONE pass over the inputs: the union
+// kernel sees, in its last merge level, how many files hold every key (the length of the run of equal keys), which is all
+// inter (run = nf) and diff (run = 1, key in file 0) need.  outK capacity >= sum of the lengths, outI / outD >= n[0].
+// Same fall-back contract as ukm_nway_union.
+int ukm_nway_union3(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, int nf, uint64_t* outK, size_t* n_out, uint64_t* outI,
+                    size_t* n_i, uint64_t* outD, size_t* n_d, bool* fell_back) {
+    *n_i = *n_d = 0;
+    ukm_tmp tmp(ctx);
+    const size_t n_masks = (n[0] + 63) / 64;
+    unsigned long long* d_masks = nullptr;
+    UKM_TRY(tmp.alloc(&d_masks, 2 * n_masks + 2));
+    UKM_CUDA(ctx, cudaMemsetAsync(d_masks, 0, (2 * n_masks + 2) * sizeof(unsigned long long), ctx->stream));
+    UKM_TRY(nway_run(ctx, NWOP_UNION, "setop_inter_diff_union_nway", keys, n, nf, outK, n_out, fell_back, d_masks, d_masks + n_masks + 1));
+    if (*fell_back) return UKM_OK;
+    {
+        ukm_stat_scope st(ctx, "setop_mask_gather", (double)n_masks * 16.0);
+        UKM_TRY(ukm_masks_gather(ctx, tmp, d_masks, n_masks, keys[0], outI, n_i));
+        UKM_TRY(ukm_masks_gather(ctx, tmp, d_masks + n_masks + 1, n_masks, keys[0], outD, n_d));
+    }
+    if (ctx->stats_on && !ctx->pending.empty()) ctx->pending.back().bytes += (double)(*n_i + *n_d) * 16.0;
+    return UKM_OK;
 }

@@ -1451,6 +1451,47 @@ int fused_inter_diff(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags,
     return UKM_OK;
 }
 
+// union, inter AND diff of the same sorted device-resident spans from one pass (nway.cu: the union kernel's last merge
+// level sees how many files hold every key).  Same applicability rules as fused_inter_diff, 3..8 files.
+int fused_union_inter_diff(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, bool shard, ukm_span* out_u, ukm_span* out_i,
+                           ukm_span* out_d, bool* done) {
+    *done = false;
+    const char* e = getenv("UKM_FUSE3");
+    if ((e && e[0] == '0') || !ukm_nway_enabled() || n_in < 3 || n_in > NW_FANIN) return UKM_OK;
+    size_t total = 0;
+    for (int f = 0; f < n_in; ++f) {
+        if (in[f].where != UKM_DEVICE || !in[f].sorted) return UKM_OK;
+        if (!shard && in[f].n == 0) return UKM_OK;
+        total += in[f].n;
+    }
+    if (in[0].n == 0) return UKM_OK;
+    const uint64_t* ks[NW_FANIN];
+    size_t ns[NW_FANIN];
+    for (int f = 0; f < n_in; ++f) {
+        ks[f] = in[f].keys;
+        ns[f] = in[f].n;
+        if ((flags & UKM_F_VALIDATE) && in[f].n > 1) UKM_TRY(ukm_dev_check_sorted_unique(ctx, in[f].keys, in[f].n));
+    }
+    ukm_tmp tmp(ctx);
+    uint64_t *d_u = nullptr, *d_i = nullptr, *d_d = nullptr;
+    if (out_u->where == UKM_DEVICE && out_u->cap >= total && out_u->keys) d_u = out_u->keys;
+    else UKM_TRY(tmp.alloc(&d_u, total + 2));
+    if (out_i->where == UKM_DEVICE && out_i->cap >= in[0].n && out_i->keys) d_i = out_i->keys;
+    else UKM_TRY(tmp.alloc(&d_i, in[0].n + 2));
+    if (out_d->where == UKM_DEVICE && out_d->cap >= in[0].n && out_d->keys) d_d = out_d->keys;
+    else UKM_TRY(tmp.alloc(&d_d, in[0].n + 2));
+    size_t n_u = 0, n_i = 0, n_d = 0;
+    bool fell_back = false;
+    UKM_TRY(ukm_nway_union3(ctx, ks, ns, n_in, d_u, &n_u, d_i, &n_i, d_d, &n_d, &fell_back));
+    if (fell_back) return UKM_OK;
+    UKM_TRY(ukm_check_dev_error(ctx, "ukm_setops_stream(union+inter+diff)"));
+    UKM_TRY(ukm_deliver(ctx, d_u, nullptr, n_u, out_u));
+    UKM_TRY(ukm_deliver(ctx, d_i, nullptr, n_i, out_i));
+    UKM_TRY(ukm_deliver(ctx, d_d, nullptr, n_d, out_d));
+    *done = true;
+    return UKM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // streamed operations on HOST inputs: every input byte crosses PCIe once, uploads / kernels / downloads overlap
 // ---------------------------------------------------------------------------------------------------
@@ -1511,10 +1552,11 @@ int stream_run(ukm_ctx* ctx, const ukm_span* in, int n_in, const int* ops, int n
     for (int k = 0; k < n_ops; ++k)
         if (ops[k] == UKM_OP_INTER && in[0].n == 0)
             return ukm_fail(ctx, UKM_E_PANIC, "ukm_setops_stream: first input is empty (inter.go:208 panics)");
-    int k_inter = -1, k_diff = -1;  // the first inter and the first diff of the call: candidates for the fused pass
+    int k_inter = -1, k_diff = -1, k_union = -1;  // the first of each kind: candidates for the fused passes
     for (int k = n_ops - 1; k >= 0; --k) {
         if (ops[k] == UKM_OP_INTER) k_inter = k;
         if (ops[k] == UKM_OP_DIFF) k_diff = k;
+        if (ops[k] == UKM_OP_UNION) k_union = k;
     }
     // buffers: the largest range decides
     size_t max_in = 0, max_f0 = 0;
@@ -1582,7 +1624,25 @@ int stream_run(ukm_ctx* ctx, const ukm_span* in, int n_in, const int* ops, int n
         }
         size_t n_res[8] = {0};
         bool have[8] = {false};
-        if (k_inter >= 0 && k_diff >= 0 && n_inter == n_in) {
+        if (k_inter >= 0 && k_diff >= 0 && k_union >= 0 && n_inter == n_in) {
+            // all three results of the range from one pass over its slices
+            ukm_span ou, oi, od;
+            memset(&ou, 0, sizeof ou);
+            memset(&oi, 0, sizeof oi);
+            memset(&od, 0, sizeof od);
+            ou.keys = d_out[q][k_union]; ou.cap = cap_out[k_union]; ou.where = UKM_DEVICE;
+            oi.keys = d_out[q][k_inter]; oi.cap = cap_out[k_inter]; oi.where = UKM_DEVICE;
+            od.keys = d_out[q][k_diff]; od.cap = cap_out[k_diff]; od.where = UKM_DEVICE;
+            bool done = false;
+            status = fused_union_inter_diff(ctx, dsp.data(), n_in, flags, true, &ou, &oi, &od, &done);
+            if (status == UKM_OK && done) {
+                n_res[k_union] = ou.n;
+                n_res[k_inter] = oi.n;
+                n_res[k_diff] = od.n;
+                have[k_union] = have[k_inter] = have[k_diff] = true;
+            }
+        }
+        if (status == UKM_OK && !have[k_inter >= 0 ? k_inter : 0] && k_inter >= 0 && k_diff >= 0 && n_inter == n_in) {
             // inter and diff of the range in one pass over its slices
             ukm_span oi, od;
             memset(&oi, 0, sizeof oi);
@@ -1724,7 +1784,15 @@ extern "C" int ukm_setops_stream(ukm_ctx* ctx, const ukm_span* in, int n_in, con
             if (ops[k] == UKM_OP_INTER) k_inter = k;
             if (ops[k] == UKM_OP_DIFF) k_diff = k;
         }
-        if (dev && k_inter >= 0 && k_diff >= 0) {
+        int k_union = -1;
+        for (int k = n_ops - 1; k >= 0; --k)
+            if (ops[k] == UKM_OP_UNION) k_union = k;
+        if (dev && k_inter >= 0 && k_diff >= 0 && k_union >= 0) {
+            bool done = false;
+            UKM_TRY(fused_union_inter_diff(ctx, in, n_in, flags, (flags & UKM_F_SHARD) != 0, &outs[k_union], &outs[k_inter], &outs[k_diff], &done));
+            if (done) have[k_union] = have[k_inter] = have[k_diff] = true;
+        }
+        if (dev && k_inter >= 0 && k_diff >= 0 && !have[k_inter]) {
             bool done = false;
             UKM_TRY(fused_inter_diff(ctx, in, n_in, flags, (flags & UKM_F_SHARD) != 0, &outs[k_inter], &outs[k_diff], &done));
             if (done) have[k_inter] = have[k_diff] = true;
