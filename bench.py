@@ -406,7 +406,16 @@ def main():
         per_op = {k: {"ms_per_op": v["ms"] / v["launches"], "algo_GB_per_op": v["algo_bytes"] / v["launches"] / 1e9,
                       "achieved_GBps": v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9, "frac": v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9 / peak}
                   for k, v in so.items() if v["ms"] and v["launches"]}
+        # bytes the dominant launch really moves (DRAM): inputs once + the union's output for the fused call; = algorithmic otherwise
+        moved = None
+        if dom_name == "setop_inter_diff_union_nway" and dom["launches"]:
+            moved = (dom["algo_bytes"] / dom["launches"]) - 2.0 * 8.0 * (total_in / world if world > 1 else total_in)
         roofline = {"bound": "hbm", "kernel": kernel_of.get(dom_name, dom_name), "family": dom_name,
+                    "algorithmic_bytes_definition": "SURVEY.md 8(d), per operation: every input key read once + every output key written once; "
+                                                    "one launch of the fused kernel does three operations (union, inter, diff)",
+                    "bytes_moved_per_launch": moved,
+                    "achieved_on_bytes_moved": (moved / (dom["ms"] / dom["launches"] * 1e-3) / 1e9) if moved else None,
+                    "frac_on_bytes_moved": (moved / (dom["ms"] / dom["launches"] * 1e-3) / 1e9 / peak) if moved and peak else None,
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                     "traffic": traffic, "peak_source": peak_src, "launches": dom["launches"],
                     "avg_launch_ms": dom["ms"] / dom["launches"] if dom["launches"] else None,

@@ -212,6 +212,22 @@ constexpr int nw_x_elems() {  // the second shared-memory region: merge buffer X
     return OP == NWOP_UNION ? SH::X_E : (SH::CAP + 7) / 8 + 1 + 2 * (((SH::CAP + 3) & ~3) / 4) + 2;
 }
 
+// inter / diff riding along the union: set the bit of key x in the mask of the intersection (one = false) or of the
+// difference (one = true) if x is one of file 0's n0 keys of the tile at f0 (global position g0 of the first)
+__device__ __forceinline__ void nw_mark_f0(const uint64_t* f0, int n0, long long g0, uint64_t x, bool one, unsigned long long* mask_i,
+                                           unsigned long long* mask_d) {
+    int lo_ = 0, hi_ = n0;  // lower_bound of x
+    while (lo_ < hi_) {
+        const int mid = (lo_ + hi_) >> 1;
+        if (f0[mid] < x) lo_ = mid + 1;
+        else hi_ = mid;
+    }
+    if (lo_ < n0 && f0[lo_] == x) {
+        const unsigned long long idx = (unsigned long long)(g0 + lo_);
+        atomicOr((one ? mask_d : mask_i) + (idx >> 6), 1ull << (idx & 63));
+    }
+}
+
 template <int OP, int NWAY, int NT, int VT, int SLOTS, int MINB, int DEFER = 1>
 __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p) {
     using SH = NwShape<NWAY, NT, VT>;
@@ -449,46 +465,45 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
                 emitmask = nw_walk_unique<VT>(A, pr.lenA, B, pr.lenB, a, diag - a, steps, outk);
                 last_steps = steps > 0 ? steps : 0;
                 // the leading keys that were not emitted continue the run the thread before started
-                if (p.mask_i) s_lead[tid] = (unsigned char)(emitmask ? __ffs(emitmask) - 1 : last_steps);
+                // the run heads among the first 8 positions (positions past the range count as heads: the tile ends there)
+                if (p.mask_i) s_lead[tid] = (unsigned char)((emitmask | (~0u << last_steps)) & 0xffu);
             }
             }  // union
+            // block scan of the distinct-key counts (group_excl_scan_u32, spelled out: the candidates of the riding inter / diff
+            // are collected between its two barriers, looked up after the second -- no barrier of their own)
             unsigned tile_total;
-            off = group_excl_scan_u32<NT>((unsigned)__popc(emitmask), (unsigned)tid, s_scan, &tile_total, 1);
-            if constexpr (OP == NWOP_UNION) {
-                if (p.mask_i) {
-                    // inter / diff ride along: a run of equal keys has one key per file that holds it (the inputs are
-                    // duplicate-free), so a run as long as the file count is a key of the intersection, and a run of one
-                    // whose key sits in file 0 is a key of the difference.  Runs are at most nf <= 8 < VT keys long: one that
-                    // starts here can only continue into the NEXT thread (s_lead, published before the scan's barriers).
-                    // The candidates (few: a run of nf or of 1) go to a list; then one thread per candidate finds the key's
-                    // position in file 0 -- the bit to set -- by binary search in file 0's keys of the tile.
-                    const int n0 = g.n[0];
-                    // file 0's keys of the tile: still in the slot (one or two levels), the copy made before level 1 (three
-                    // levels), or -- the copy did not fit -- the global array
-                    const uint64_t* f0 = LEVELS < 3 ? slot + g.off[0] : (n0 <= F0CAP ? s_f0 : s_fk[0] + s_g0[s]);
-                    auto mark = [&](uint64_t x, bool one) {
-                        int lo_ = 0, hi_ = n0;  // lower_bound of x in file 0's segment
-                        while (lo_ < hi_) {
-                            const int mid = (lo_ + hi_) >> 1;
-                            if (f0[mid] < x) lo_ = mid + 1;
-                            else hi_ = mid;
-                        }
-                        if (lo_ < n0 && f0[lo_] == x) {
-                            const unsigned long long idx = (unsigned long long)(s_g0[s] + lo_);
-                            atomicOr((one ? p.mask_d : p.mask_i) + (idx >> 6), 1ull << (idx & 63));
-                        }
-                    };
-                    const int lead_next = tid + 1 < NT ? (int)s_lead[tid + 1] : 0;
-                    const int nfiles = p.F.nf;
-                    // (a warp-uniform loop over the VT positions with ballot-aggregated list appends was measured slower:
-                    // 45.1 against 40.6 ms per C3 call)
-                    unsigned m = emitmask;
-                    while (m) {
-                        const int b0 = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int nxt = m ? __ffs(m) - 1 : last_steps + lead_next;
-                        const int len = nxt - b0;
-                        if (len == nfiles || len == 1) {
+            {
+                const unsigned cnt_ = (unsigned)__popc(emitmask);
+                const unsigned incl_ = warp_incl_scan_u32(cnt_);
+                const unsigned w_ = (unsigned)tid >> 5;
+                if (lane == 31) s_scan[w_] = incl_;
+                named_bar_sync(1, NT);  // every s_lead is visible too
+                if constexpr (OP == NWOP_UNION) {
+                    if (p.mask_i) {
+                        // inter / diff ride along: a run of equal keys has one key per file that holds it (the inputs are
+                        // duplicate-free), so a run as long as the file count is a key of the intersection, and a run of one
+                        // whose key sits in file 0 is a key of the difference.  Runs are at most nf <= 8 < VT keys long: one
+                        // that starts here can only continue into the NEXT thread (s_lead).  The candidates (few: a run of
+                        // nf or of 1) go to a list; after the second barrier one thread per candidate finds the key's position
+                        // in file 0 -- the bit to set -- by binary search in file 0's keys of the tile.
+                        const int n0 = g.n[0];
+                        // file 0's keys of the tile: still in the slot (one or two levels), the copy made before level 1 (three
+                        // levels), or -- the copy did not fit -- the global array
+                        const uint64_t* f0 = LEVELS < 3 ? slot + g.off[0] : (n0 <= F0CAP ? s_f0 : s_fk[0] + s_g0[s]);
+                        // the run heads of this range followed by those of the next thread's first positions: a head at i with
+                        // the next head at i + 1 is a run of one, with the next head at i + nf a run of nf (no loop over heads)
+                        const unsigned next_heads = tid + 1 < NT ? (unsigned)s_lead[tid + 1] : 0xffu;
+                        const int nfiles = p.F.nf;
+                        const unsigned range = last_steps >= 32 ? ~0u : ((1u << last_steps) - 1u);
+                        const unsigned ext = (emitmask & range) | (next_heads << last_steps);
+                        unsigned run_nf = ext & (ext >> nfiles);
+                        for (int k = 1; k < nfiles; ++k) run_nf &= ~(ext >> k);
+                        const unsigned run_one = ext & (ext >> 1);
+                        unsigned m = (run_nf | run_one) & range;
+                        while (m) {  // rarely more than one iteration
+                            const int b0 = __ffs(m) - 1;
+                            m &= m - 1;
+                            const bool one = (run_one >> b0) & 1u;
                             uint64_t x = outk[0];
 #pragma unroll
                             for (int it = 1; it < VT; ++it)
@@ -496,15 +511,29 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
                             const int pos = atomicAdd(&s_ncand, 1);
                             if (pos < NCAND) {
                                 s_ckey[pos] = x;
-                                s_cone[pos] = len == 1;
+                                s_cone[pos] = one;
                             } else {
-                                mark(x, len == 1);  // more candidates than the list holds (files that barely overlap): in place
+                                nw_mark_f0(f0, n0, s_g0[s], x, one, p.mask_i, p.mask_d);  // more candidates than the list holds: in place
                             }
                         }
                     }
-                    named_bar_sync(1, NT);  // the list is complete
+                }
+                if (w_ == 0) {
+                    const unsigned x_ = (lane < (unsigned)NW) ? s_scan[lane] : 0u;
+                    const unsigned xi_ = warp_incl_scan_u32(x_);
+                    if (lane < (unsigned)NW) s_scan[lane] = xi_ - x_;
+                    if (lane == NW - 1) s_scan[NW] = xi_;
+                }
+                named_bar_sync(1, NT);  // the candidate list is complete
+                tile_total = s_scan[NW];
+                off = s_scan[w_] + incl_ - cnt_;
+            }
+            if constexpr (OP == NWOP_UNION) {
+                if (p.mask_i) {
+                    const int n0 = g.n[0];
+                    const uint64_t* f0 = LEVELS < 3 ? slot + g.off[0] : (n0 <= F0CAP ? s_f0 : s_fk[0] + s_g0[s]);
                     const int nc = s_ncand < NCAND ? s_ncand : NCAND;
-                    for (int j = tid; j < nc; j += NT) mark(s_ckey[j], s_cone[j] != 0);
+                    for (int j = tid; j < nc; j += NT) nw_mark_f0(f0, n0, s_g0[s], s_ckey[j], s_cone[j] != 0, p.mask_i, p.mask_d);
                     // file 0's keys were read from the slot, which the staging below overwrites
                     if (LEVELS < 3) named_bar_sync(1, NT);
                 }
@@ -719,6 +748,14 @@ int ukm_nway_union3(ukm_ctx* ctx, const uint64_t* const* keys, const size_t* n, 
     UKM_CUDA(ctx, cudaMemsetAsync(d_masks, 0, (2 * n_masks + 2) * sizeof(unsigned long long), ctx->stream));
     UKM_TRY(nway_run(ctx, NWOP_UNION, "setop_inter_diff_union_nway", keys, n, nf, outK, n_out, fell_back, d_masks, d_masks + n_masks + 1));
     if (*fell_back) return UKM_OK;
+    // algorithmic bytes are per OPERATION: every input key read once + every output key written once for each
+    // of union, inter and diff.  nway_run recorded the union's; the launch also did the work of the other two (whose outputs
+    // are added by the gather below).  The bytes actually moved are the union's alone -- the three share one read.
+    if (ctx->stats_on && !ctx->pending.empty()) {
+        double in_bytes = 0;
+        for (int f = 0; f < nf; ++f) in_bytes += (double)n[f] * 8.0;
+        ctx->pending.back().bytes += 2.0 * in_bytes;
+    }
     {
         ukm_stat_scope st(ctx, "setop_mask_gather", (double)n_masks * 16.0);
         UKM_TRY(ukm_masks_gather(ctx, tmp, d_masks, n_masks, keys[0], outI, n_i));
