@@ -427,6 +427,28 @@ def main():
                                           "share_of_step": so_ms / (ms_step * args.steps) if ms_step else None}}
 
         # ---- e2e: same step through the C ABI with HOST buffers (pinned), H2D + D2H in the timed region ----
+        # ---- N > 1: how fast the copy engines pull a step's remote slices, under the kernels and alone ----
+        exchange = None
+        if pex is not None:
+            torch.cuda.synchronize()
+            barrier()
+            pex.time_pulls, pex.pull_marks = True, []
+            step()  # the pulls recorded are those of the NEXT step's pieces, queued while this step's kernels run
+            loaded = pex.pull_timing()
+            barrier()
+            pex.pull_marks = []
+            gen = pex.exchange_chunks()
+            next(gen)  # hands out the piece pulled above and queues the next pulls: nothing else runs on the GPU
+            idle = pex.pull_timing()
+            gen.close()
+            barrier()
+            pex.time_pulls, pex.pull_marks = False, []
+            exchange = {"copy_streams": len(pex.streams), "pieces_per_slice": pex.split, "under_kernels": loaded, "gpu_idle": idle,
+                        "note": "rank 0's peer copies of one step (CUDA events around every copy); span_ms = first start to last end"}
+            for d in (loaded, idle):
+                if d:
+                    d["GBps_over_span"] = d["bytes"] / max(d["span_ms"], 1e-9) / 1e6
+
         e2e = None
         if not args.no_e2e:
             hfiles = {f: torch.empty(t.shape[0], dtype=torch.int64, pin_memory=True) for f, t in local_files.items()}
@@ -549,7 +571,7 @@ def main():
                                         "kernels run on the current one; the exchange plan is made once"
                                         if pex is not None else "one NCCL all-to-all-v per step")),
                        "kmers_per_step": 3 * total_in},
-            "roofline": roofline, "three_separate_calls": separate, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "three_separate_calls": separate, "cpu_baseline": cpu, "e2e": e2e, "exchange": exchange, "gpu_launches": int(launches), "clocks": clocks,
             "check": check,
             "per_kernel": {k: {"launches": v["launches"], "ms": round(v["ms"], 3),
                                "GBps": round(v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] else None}

@@ -17,6 +17,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Sequence
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -148,8 +150,18 @@ class PeerPullExchange:
     """
 
     def __init__(self, backend, rank: int, world: int, local_files: Dict[int, torch.Tensor], n_files: int, group=None,
-                 n_streams: int = 4):
+                 n_streams: int = 0, split: int = 0):
         from torch.multiprocessing.reductions import reduce_tensor
+        # copy-engine parallelism: one peer copy keeps one engine busy, several in flight on different streams add up
+        # until the link is full.  UKM_PULL_STREAMS / UKM_PULL_SPLIT override (streams; pieces one file's slice is cut into)
+        n_streams = int(n_streams or os.environ.get("UKM_PULL_STREAMS", "8"))
+        self.split = max(1, int(split or os.environ.get("UKM_PULL_SPLIT", "1")))
+        # a peer copy is queued on a stream of the OWNER's device (torch's rule for cross-device copies): with one stream per
+        # owner its files travel one after the other; two per owner measured 12.7 instead of 13.9 ms per C3 step at N = 4,
+        # where the 6 GB a rank pulls per step bound the step (profiles/r02_exp_pull_n4.md)
+        self.per_src = max(1, int(os.environ.get("UKM_PULL_SRC_STREAMS", "2")))
+        self.src_streams: Dict[tuple, torch.cuda.Stream] = {}
+        self.src_next: Dict[int, int] = {}
         self.backend, self.rank, self.world, self.group, self.n_files = backend, rank, world, group, n_files
         self.local = local_files
         self.device = next(iter(local_files.values())).device
@@ -205,8 +217,10 @@ class PeerPullExchange:
     def wait(self, events, files):
         cur = torch.cuda.current_stream(self.device)
         for f in files:
-            if events[f] is not None:
-                cur.wait_event(events[f])
+            if events[f] is None:
+                continue
+            for e in (events[f] if isinstance(events[f], (list, tuple)) else (events[f],)):
+                cur.wait_event(e)
 
     # ---- pipelined form: the rank's key range in `chunks` pieces, piece c + 1 pulled while piece c is computed ----
     def plan_chunks(self, splitters: np.ndarray, chunks: int, key_hi: int = 1 << 62):
@@ -228,6 +242,21 @@ class PeerPullExchange:
         self.chunk_prefetched = None
         self.prefetch_next_step = True
         self.chunk_seq = 0
+        self.time_pulls = False  # measurement: keep (start, end, bytes) events of every peer copy in pull_marks
+        self.pull_marks: list = []
+
+    def pull_timing(self):
+        """(bytes, ms, GB/s) of the peer copies recorded since time_pulls was set: first start to last end."""
+        if not self.pull_marks:
+            return None
+        torch.cuda.synchronize(self.device)
+        t_ref = self.pull_marks[0][0]
+        lo = min(t_ref.elapsed_time(t0) for t0, _, _ in self.pull_marks)
+        hi = max(t_ref.elapsed_time(e) for _, e, _ in self.pull_marks)
+        busy = sum(t0.elapsed_time(e) for t0, e, _ in self.pull_marks)
+        nbytes = sum(b for _, _, b in self.pull_marks)
+        return {"bytes": nbytes, "copies": len(self.pull_marks), "span_ms": hi - lo, "sum_copy_ms": busy,
+                "GBps_per_copy": nbytes / max(busy, 1e-9) / 1e6}
 
     def exchange_chunks(self):
         """Generator over the pieces of this rank's key range: yields (slices, events) like exchange_async.  The pulls
@@ -253,14 +282,36 @@ class PeerPullExchange:
                 if buf is None or buf.shape[0] < n:
                     buf = torch.empty(int(n * 1.05) + 16, dtype=self.peer[f].dtype, device=self.device)
                     self.chunk_bufs[(f, q)] = buf
-                s = self.streams[i % len(self.streams)]
-                i += 1
-                if self.chunk_done[q] is not None:
-                    s.wait_event(self.chunk_done[q])
-                with torch.cuda.stream(s):
-                    buf[:n].copy_(self.peer[f][lo:hi], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(s)
+                evs = []
+                for part in range(self.split):  # a slice may be cut into pieces that travel on different copy engines
+                    a, b = n * part // self.split, n * (part + 1) // self.split
+                    if b <= a and part:
+                        continue
+                    s = self.streams[i % len(self.streams)]
+                    i += 1
+                    if self.chunk_done[q] is not None:
+                        s.wait_event(self.chunk_done[q])
+                    with torch.cuda.stream(s):
+                        if self.time_pulls:
+                            t0 = torch.cuda.Event(enable_timing=True)
+                            t0.record(s)
+                        if self.per_src <= 1:  # torch: the copy runs on the OWNER device's current stream of this process
+                            buf[a:b].copy_(self.peer[f][lo + a:lo + b], non_blocking=True)
+                        else:  # ... on one of per_src streams of the owner device, so copies from one owner overlap
+                            od = self.peer[f].device
+                            j = self.src_next.get(od.index, 0)
+                            self.src_next[od.index] = j + 1
+                            key = (od.index, j % self.per_src)
+                            if key not in self.src_streams:
+                                self.src_streams[key] = torch.cuda.Stream(device=od)
+                            with torch.cuda.stream(self.src_streams[key]):
+                                buf[a:b].copy_(self.peer[f][lo + a:lo + b], non_blocking=True)
+                        e = torch.cuda.Event(enable_timing=self.time_pulls)
+                        e.record(s)
+                    if self.time_pulls:
+                        self.pull_marks.append((t0, e, (b - a) * 8))
+                    evs.append(e)
+                ev = evs
                 slices[f] = buf[:n]
                 events[f] = ev
             return slices, events, q
