@@ -103,6 +103,27 @@ if os.path.exists(lp):
     for k, v in traffic.items():
         if isinstance(v, dict):
             lines.append(f"* `{k}`: {v['dram_bytes_per_launch'] / 1e9:.2f} GB per call ({v['kernels']})")
+    # one fused step, launch by launch: the share of every kernel in the step (to be compared with bench.py's
+    # roofline.share_of_step, which comes from CUDA events in an unprofiled run)
+    if fused:
+        i1 = idx[id(fused[-1])]
+        i0 = i1
+        while i0 > 0 and L[i0 - 1]["kernel"].startswith(("nway_partition_kernel", "nway_check_kernel")):
+            i0 -= 1
+        i2 = i1
+        while i2 + 1 < len(L) and L[i2 + 1]["kernel"].startswith(("nfilter_count_kernel", "nfilter_scan_kernel", "nfilter_gather_kernel")):
+            i2 += 1
+        step = L[i0:i2 + 1]
+        st = sum(d.get("ms", 0) for d in step)
+        lines += ["", f"One step of the bench (= one `ukm_setops_stream` call: launches {i0}..{i2} of the list), under ncu:", "",
+                  "| # | kernel | ms | share of the step | DRAM read GB | DRAM write GB |", "|---:|---|---:|---:|---:|---:|"]
+        for j, d in enumerate(step):
+            lines.append(f"| {i0 + j} | `{d['kernel']}` | {d.get('ms', 0):.3f} | {d.get('ms', 0) / st * 100:.1f}% | "
+                         f"{d.get('dram__bytes_read.sum', 0) / 1e9:.2f} | {d.get('dram__bytes_write.sum', 0) / 1e9:.2f} |")
+        fam = sum(d.get("ms", 0) for d in step if d["kernel"].startswith(("nway_", )))
+        lines += ["", f"Sum {st:.3f} ms; the fused kernel with its partition (the family bench.py reports as `setop_inter_diff_union_nway`): "
+                  f"{fam:.3f} ms = {fam / st * 100:.1f}% of the step's kernel time (bench.py, CUDA events, unprofiled: share_of_step 0.979 of the "
+                  "step's wall time including the host-side gaps)."]
     open(os.path.join(PROF, f"{tag}_launch_summary.md"), "w").write("\n".join(lines) + "\n")
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
