@@ -9,9 +9,13 @@ Workload (BASELINE.json configs[2], "C3" in SURVEY.md 8d): 8 sorted duplicate-fr
 One STEP = `inter` + `diff` + `union` over the 8 files (each op consumes all ~4e9 input
 k-mers); value = (3 * sum |F_i|) / step time, inputs resident in HBM.
 
-N > 1 (strong scaling: same total work): file f starts on rank f mod N; every step does one
-grouped NCCL all-to-all-v by key range (unikmer_b200/dist.py) and then the three operations
-on each rank's bucket; results stay sharded in rank order.
+A step is ONE call of the C ABI (ukm_setops_stream): the three results come out of one pass over
+the inputs; the same step as three calls is reported beside it.
+
+N > 1 (strong scaling: same total work): file f lives on rank f mod N; every rank owns a key range,
+pulls its slice of the remote files over NVLink (CUDA-IPC peer copies on the copy engines, double
+buffered, the plan made once: unikmer_b200/dist.py) while the kernels run on the slices that have
+arrived, and makes the same single ABI call on them; results stay sharded in rank order.
 
 --impl reference: the reference's CPU algorithms for the same path (hash-map union,
 two-pointer inter/diff; oracle/oracle.c -- the Go reference cannot be built in this image)
@@ -185,6 +189,12 @@ def main():
     args.universe, args.ref_universe, args.cpu_universe = int(args.universe), int(args.ref_universe), int(args.cpu_universe)
     if args.impl == "reference":
         return run_reference(args)
+
+    # Use the first N GPUs of the box and nothing else (at N = 2 / 4 on an 8-GPU box the other GPUs showed
+    # activity -- contexts created by peer-access probing); a launcher that already restricts the devices is left alone.
+    if "CUDA_VISIBLE_DEVICES" not in os.environ:
+        n_local = int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0) or max(1, args.gpus)
+        os.environ["CUDA_VISIBLE_DEVICES"] = ",".join(str(i) for i in range(n_local))
 
     import torch
     import torch.distributed as dist
