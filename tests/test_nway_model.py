@@ -32,3 +32,16 @@ def test_rows_host_model(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "rows model ok" in out.stdout and " 0 with a bank conflict" in out.stdout
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_ride_along_host_model(tmp_path):
+    """`inter` / `diff` riding along the union's last level: the run-length bit arithmetic the kernel uses
+    (nw_lead_heads / nw_run_candidates, nway_core.cuh) laid over the kernel's thread ranges -- every tile shape, 2..8 files,
+    identical / disjoint / empty files, runs placed at every offset against the thread boundaries -- against set algebra."""
+    exe = tmp_path / "ride_model"
+    src = os.path.join(ROOT, "tests", "host", "ride_model.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", src, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "ride-along model ok" in out.stdout

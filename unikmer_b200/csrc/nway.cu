@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
                 last_steps = steps > 0 ? steps : 0;
                 // the leading keys that were not emitted continue the run the thread before started
                 // the run heads among the first 8 positions (positions past the range count as heads: the tile ends there)
-                if (p.mask_i) s_lead[tid] = (unsigned char)((emitmask | (~0u << last_steps)) & 0xffu);
+                if (p.mask_i) s_lead[tid] = (unsigned char)nw_lead_heads(emitmask, last_steps);
             }
             }  // union
             // block scan of the distinct-key counts (group_excl_scan_u32, spelled out: the candidates of the riding inter / diff
@@ -490,16 +490,9 @@ __global__ void __launch_bounds__(NT + NWK_AUX, MINB) nway_kernel(const NwArgs p
                         // file 0's keys of the tile: still in the slot (one or two levels), the copy made before level 1 (three
                         // levels), or -- the copy did not fit -- the global array
                         const uint64_t* f0 = LEVELS < 3 ? slot + g.off[0] : (n0 <= F0CAP ? s_f0 : s_fk[0] + s_g0[s]);
-                        // the run heads of this range followed by those of the next thread's first positions: a head at i with
-                        // the next head at i + 1 is a run of one, with the next head at i + nf a run of nf (no loop over heads)
                         const unsigned next_heads = tid + 1 < NT ? (unsigned)s_lead[tid + 1] : 0xffu;
-                        const int nfiles = p.F.nf;
-                        const unsigned range = last_steps >= 32 ? ~0u : ((1u << last_steps) - 1u);
-                        const unsigned ext = (emitmask & range) | (next_heads << last_steps);
-                        unsigned run_nf = ext & (ext >> nfiles);
-                        for (int k = 1; k < nfiles; ++k) run_nf &= ~(ext >> k);
-                        const unsigned run_one = ext & (ext >> 1);
-                        unsigned m = (run_nf | run_one) & range;
+                        unsigned run_nf, run_one;
+                        unsigned m = nw_run_candidates(emitmask, last_steps, next_heads, p.F.nf, &run_nf, &run_one);
                         while (m) {  // rarely more than one iteration
                             const int b0 = __ffs(m) - 1;
                             m &= m - 1;

@@ -288,6 +288,32 @@ NW_HD int nw_merge_path_g(const uint64_t* A, int na, const uint64_t* B, int nb, 
     return lo;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// inter / diff riding along the last level (nway.cu): run lengths from emit masks
+// ---------------------------------------------------------------------------------------------------
+// A thread's last-level range holds `steps` merged keys; bit i of `emitmask` = key i starts a run of equal keys (a run
+// has one key per file that holds the k-mer: the inputs are duplicate-free).  Runs are at most nf <= 8 keys long, so one
+// that starts in this range ends in it or in the first 8 positions of the next thread's range.
+// What a thread publishes for its predecessor: the run heads among its first 8 positions; positions past the end of
+// its range count as heads (the tile ends there, so does any run).
+NW_HD unsigned nw_lead_heads(unsigned emitmask, int steps) { return (emitmask | (~0u << steps)) & 0xffu; }
+
+// Candidates of the range: bit i of *run_nf = a run of exactly nf keys starts at i (the key is in every file),
+// bit i of *run_one = a run of one key starts at i (the key is in one file only).  next_heads = nw_lead_heads of
+// the next thread (0xff behind the last thread).  Returns the union of the two masks.
+NW_HD unsigned nw_run_candidates(unsigned emitmask, int steps, unsigned next_heads, int nf, unsigned* run_nf, unsigned* run_one) {
+    const unsigned range = steps >= 32 ? ~0u : ((1u << steps) - 1u);
+    // the heads of this range followed by those of the next thread's first positions: a head at i with the next head
+    // at i + 1 is a run of one, with the next head at i + nf a run of nf (no loop over the heads)
+    const unsigned ext = (emitmask & range) | (next_heads << steps);
+    unsigned rn = ext & (ext >> nf);
+    for (int k = 1; k < nf; ++k) rn &= ~(ext >> k);
+    const unsigned ro = ext & (ext >> 1);
+    *run_nf = rn;
+    *run_one = ro;
+    return (rn | ro) & range;
+}
+
 // which pair of a level does thread `tid` work on (-1: none), and its index inside the pair
 template <int NPAIRS>
 NW_HD int nw_find_pair(const int* tb, int tid, int* j) {
