@@ -45,3 +45,17 @@ def test_ride_along_host_model(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "ride-along model ok" in out.stdout
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_nfilter_search_host_model(tmp_path):
+    """The per-lane searches of the single-pass inter / diff filter (unikmer_b200/csrc/nfilter_core.cuh: clamped straight-line
+    probes with a warp-uniform depth): every segment length 0..300 and around the powers of two up to 2200, every admissible
+    depth, keys on and between the elements -- against std::binary_search / std::lower_bound, with every probe address
+    checked to stay inside its segment."""
+    exe = tmp_path / "nfilter_model"
+    src = os.path.join(ROOT, "tests", "host", "nfilter_model.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", src, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "nfilter model ok" in out.stdout and "none outside its segment" in out.stdout
