@@ -107,3 +107,17 @@ def test_cli_view_and_info_need_no_gpu(tmp_path):
     assert out[:3] == ["AAAAA\t7", "AAAAC\t8", "TTTTT\t9"]
     info = subprocess.run([unik.CLI_PATH, "info", p], capture_output=True, text=True, check=True).stdout.strip().split("\n")
     assert info[1].split("\t")[1:] == ["5", "0", "0", "0", "1", "0", "1", "0", "3", "3"]
+
+
+def test_fastx_reader(tmp_path):
+    """The CLI's FASTA / FASTQ reader (unikmer_b200/host/fastx.hpp): wrapped records, CRLF, blanks inside sequence lines,
+    FASTQ quality lines that start with '@' or '>', truncated records -- tests/host/fastx_test.cpp."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    exe = tmp_path / "fastx_test"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "host", "fastx_test.cpp"), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "fastx ok" in out.stdout, out.stderr[-2000:]

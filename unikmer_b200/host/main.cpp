@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../../include/ukm.h"
+#include "fastx.hpp"
 #include "unik.hpp"
 
 namespace {
@@ -213,36 +214,8 @@ Taxonomy load_taxonomy(Options& o, ukm_ctx* ctx) {
 // ---- FASTA/FASTQ: bio/seqio/fastx view (line breaks stripped, case kept) ------------------------------------------
 void read_fastx(const std::string& path, std::vector<uint8_t>& bases, std::vector<uint64_t>& rec_off) {
     std::vector<uint8_t> raw = unik::slurp(path);
-    size_t i = 0, n = raw.size();
-    auto line_end = [&](size_t p) {
-        while (p < n && raw[p] != '\n') ++p;
-        return p;
-    };
-    while (i < n) {
-        if (raw[i] == '\n' || raw[i] == '\r') { ++i; continue; }
-        if (raw[i] == '>') {
-            i = line_end(i) + 1;
-            while (i < n && raw[i] != '>') {
-                size_t e = line_end(i);
-                size_t stop = e;
-                while (stop > i && (raw[stop - 1] == '\r' || raw[stop - 1] == ' ')) --stop;
-                bases.insert(bases.end(), raw.begin() + i, raw.begin() + stop);
-                i = e + 1;
-            }
-            rec_off.push_back(bases.size());
-        } else if (raw[i] == '@') {
-            i = line_end(i) + 1;
-            size_t e = line_end(i);
-            size_t stop = e;
-            while (stop > i && raw[stop - 1] == '\r') --stop;
-            bases.insert(bases.end(), raw.begin() + i, raw.begin() + stop);
-            rec_off.push_back(bases.size());
-            i = line_end(e + 1) + 1;  // '+' line
-            i = line_end(i) + 1;      // quality line
-        } else {
-            die("%s: invalid FASTA/Q record start", path.c_str());
-        }
-    }
+    const std::string err = fastx::parse(raw.data(), raw.size(), bases, rec_off);
+    if (!err.empty()) die("%s: %s", path.c_str(), err.c_str());
 }
 
 // ---- shared command plumbing -----------------------------------------------------------------------------------------
