@@ -168,12 +168,15 @@ int ukm_common(ukm_ctx* ctx, const ukm_span* in, int n_in, unsigned flags, uint1
  * key space is cut into ranges (all three are key-local), the slices of range c+1 are uploaded while the operations
  * run on range c and the results of range c-1 are downloaded.  outs[k] receives the result of ops[k]; results are
  * exactly those of ukm_inter / ukm_diff / ukm_union on the whole files (the whole-file rules -- empty first file,
- * empty later file -- are applied on the file sizes).  When both inter and diff are asked for they share ONE pass over
- * the inputs (after the first subject every key of file 0 can only still belong to one of the two results).
+ * empty later file -- are applied on the file sizes).  Operations asked for together share passes over the inputs
+ * (per key range when streamed, over the whole files when the inputs are DEVICE spans): with a union in the list,
+ * inter and diff come out of the union's pass (its last merge level sees how many files hold every key); inter and
+ * diff without a union share one filter pass (after the first subject every key of file 0 can only still belong to
+ * one of the two results).  Up to eight files per pass; more files, taxids or inputs that are not duplicate-free take
+ * the single-operation paths.
  * Keys only (flags: 0, UKM_F_VALIDATE, UKM_F_SHARD for device-resident key-range slices); inputs all HOST /
- * HOST_PINNED (pinned memory is what lets the copies overlap: ukm_alloc_pinned) or all DEVICE (then nothing is
- * streamed and the call is the three plain calls).  ukm_inter / ukm_diff / ukm_union take the same streamed path
- * on their own when every input is in host memory. */
+ * HOST_PINNED (pinned memory is what lets the copies overlap: ukm_alloc_pinned) or all DEVICE (nothing is streamed).
+ * ukm_inter / ukm_diff / ukm_union take the same streamed path on their own when every input is in host memory. */
 typedef enum ukm_setop { UKM_OP_INTER = 0, UKM_OP_DIFF = 1, UKM_OP_UNION = 2 } ukm_setop;
 int ukm_setops_stream(ukm_ctx* ctx, const ukm_span* in, int n_in, const int* ops, int n_ops, unsigned flags,
                       ukm_span* outs);
